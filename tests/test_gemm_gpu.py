@@ -1,0 +1,102 @@
+"""tcgen05 GEMM vs torch fp32 matmul on the same bf16 inputs (all operand majors, tails, epilogues)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, dev, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).to(dev)
+
+
+def _close(got, ref, tol=2e-2):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs().max().item()
+    den = ref.abs().max().item() + 1e-6
+    assert err / den < tol, f"max err {err} vs scale {den}"
+
+
+SHAPES = [(128, 128, 64), (256, 384, 512), (300, 128, 192), (16416, 512, 512), (2, 4608, 512),
+          (1056, 1536, 512), (1024, 1024, 4096)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_kk_store(cuda_dev, M, N, K):
+    import vds_b200
+    from vds_b200 import ops
+    a, b = _mk((M, K), cuda_dev, 1), _mk((N, K), cuda_dev, 2)
+    bias = _mk((N,), cuda_dev, 3)
+    out = ops.gemm(a, b, bias=bias)
+    ref = a.float() @ b.float().t() + bias.float()
+    _close(out, ref)
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 384, 512), (300, 128, 192), (16416, 512, 1536)])
+def test_gemm_dgrad_k_mn(cuda_dev, M, N, K):
+    """dx[M,N] = dy[M,K] @ W[K,N]: A K-major, B MN-major."""
+    from vds_b200 import ops
+    dy, w = _mk((M, K), cuda_dev, 4), _mk((K, N), cuda_dev, 5)
+    out = ops.gemm(dy, w, b_mn=True)
+    _close(out, dy.float() @ w.float())
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(384, 256, 512, 1), (1536, 512, 16416, 4), (128, 128, 2, 1),
+                                          (512, 4096, 1024, 3)])
+def test_gemm_wgrad_mn_mn(cuda_dev, M, N, K, splits):
+    """dW[M,N] += dy[K,M]^T @ x[K,N]: both MN-major, fp32 accumulate, split-K."""
+    from vds_b200 import ops, lib
+    dy, x = _mk((K, M), cuda_dev, 6), _mk((K, N), cuda_dev, 7)
+    out = torch.ones((M, N), device=cuda_dev, dtype=torch.float32)
+    ops.gemm(dy, x, a_mn=True, b_mn=True, epilogue=lib.EPI_ACCUM_F32, out=out, splits=splits)
+    _close(out, 1.0 + dy.float().t() @ x.float())
+
+
+def test_gemm_mn_k(cuda_dev):
+    from vds_b200 import ops
+    a, b = _mk((512, 384), cuda_dev, 8), _mk((256, 512), cuda_dev, 9)   # a: [K,M], b: [N,K]
+    out = ops.gemm(a, b, a_mn=True)
+    _close(out, a.float().t() @ b.float().t())
+
+
+def test_gemm_bias_gelu(cuda_dev):
+    from vds_b200 import ops, lib
+    a, b, bias = _mk((528, 512), cuda_dev, 10), _mk((2048, 512), cuda_dev, 11, 0.05), _mk((2048,), cuda_dev, 12)
+    pre, act = ops.gemm(a, b, bias=bias, epilogue=lib.EPI_BIAS_GELU)
+    ref_pre = (a.float() @ b.float().t() + bias.float()).bfloat16()
+    _close(pre, ref_pre)
+    _close(act, torch.nn.functional.gelu(pre.float()), tol=1e-2)
+
+
+def test_gemm_gate_res(cuda_dev):
+    from vds_b200 import ops, lib
+    Bt, Lr, h = 2, 272, 512
+    a, w = _mk((Bt * Lr, h), cuda_dev, 13), _mk((h, h), cuda_dev, 14, 0.05)
+    x, gate = _mk((Bt * Lr, h), cuda_dev, 15), _mk((Bt, 9 * h), cuda_dev, 16)
+    g = gate[:, 2 * h:3 * h]
+    lin, xo = ops.gemm(a, w, epilogue=lib.EPI_GATE_RES, aux=x, gate=g, rows_per_batch=Lr)
+    ref_lin = (a.float() @ w.float().t()).bfloat16()
+    _close(lin, ref_lin)
+    ref = x + lin.view(Bt, Lr, h) .mul(g[:, None, :]).view(Bt * Lr, h)
+    _close(xo, ref, tol=1e-2)
+
+
+def test_gemm_dgelu(cuda_dev):
+    from vds_b200 import ops, lib
+    dy, w, h1 = _mk((528, 512), cuda_dev, 17), _mk((512, 2048), cuda_dev, 18, 0.05), _mk((528, 2048), cuda_dev, 19)
+    out = ops.gemm(dy, w, b_mn=True, epilogue=lib.EPI_DGELU, aux=h1)
+    hh = h1.float().requires_grad_(True)
+    torch.nn.functional.gelu(hh).backward(dy.float() @ w.float())
+    _close(out, hh.grad)
+
+
+def test_gemm_remap_rows(cuda_dev):
+    from vds_b200 import ops
+    Bt, Np, h = 2, 256, 512
+    a, w, bias = _mk((Bt * Np, 128), cuda_dev, 20), _mk((h, 128), cuda_dev, 21), _mk((h,), cuda_dev, 22)
+    out = torch.zeros((Bt, Np + 16, h), device=cuda_dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, bias=bias, out=out.view(-1, h), remap=(Np, Np + 16, 16))
+    ref = (a.float() @ w.float().t() + bias.float()).view(Bt, Np, h)
+    _close(out[:, 16:], ref)
+    assert out[:, :16].abs().max().item() == 0

@@ -1,0 +1,380 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T  (bf16 in, fp32 accumulate).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128-B swizzle, STAGES-deep mbarrier ring)
+//   warp 1      MMA issuer     (one thread issues tcgen05.mma 128 x BN x 16; accumulators in TMEM,
+//                               double-buffered so the epilogue of tile i overlaps the mainloop of i+1)
+//   warps 2..5  epilogue       (tcgen05.ld: thread == output row; fused bias / erf-GELU / gate+residual /
+//                               GELU' / fp32 split-K reduction)
+// Both operands may be K-major or MN-major (runtime-free: template flags), which covers fprop
+// (K,K), dgrad (K,MN) and wgrad (MN,MN) without any transpose copies.
+//
+// Replaces: every nn.Linear on the reference hot path (model.py:62-90,125-165,318-350,374-390),
+// Conv3d patch-embed as a GEMM (model.py:173-185) and their autograd (train.py:432).
+#include <cuda.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vds {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+struct GemmDev {
+  int M, N, K;
+  int splits, k_per_split;
+  void* C;
+  long long ldc;
+  void* C2;
+  long long ldc2;
+  const bf16* bias;
+  const bf16* aux;
+  long long ldaux;
+  const bf16* gate;
+  long long gate_stride;
+  int rows_per_batch;
+  int remap_rows, remap_stride, remap_offset;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float dgelu_erf(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__device__ __forceinline__ void ld8_bf16(const bf16* p, float (&o)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+}
+__device__ __forceinline__ void st8_bf16(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// One thread handles 32 consecutive columns [col0, col0+32) of output row `row`.
+template <int EPI>
+__device__ __forceinline__ void epilogue_row(const GemmDev& p, int row, int col0, const uint32_t (&raw)[32]) {
+  if (row >= p.M) return;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    if (col >= p.N) break;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(raw[g * 8 + j]);
+
+    if constexpr (EPI == VDS_EPI_ACCUM_F32) {
+      float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
+      red_add_v4(c, acc[0], acc[1], acc[2], acc[3]);
+      red_add_v4(c + 4, acc[4], acc[5], acc[6], acc[7]);
+    } else {
+      if constexpr (EPI != VDS_EPI_DGELU) {
+        if (p.bias != nullptr) {
+          float b[8];
+          ld8_bf16(p.bias + col, b);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += b[j];
+        }
+      }
+      if constexpr (EPI == VDS_EPI_STORE_F32) {
+        float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
+        *reinterpret_cast<float4*>(c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(c + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      } else if constexpr (EPI == VDS_EPI_STORE) {
+        long long orow = row;
+        if (p.remap_rows > 0)
+          orow = (long long)(row / p.remap_rows) * p.remap_stride + p.remap_offset + row % p.remap_rows;
+        st8_bf16(reinterpret_cast<bf16*>(p.C) + orow * p.ldc + col, acc);
+      } else if constexpr (EPI == VDS_EPI_BIAS_GELU) {
+        float act[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] = bf16_round(acc[j]);
+          act[j] = gelu_erf(acc[j]);
+        }
+        if (p.C != nullptr) st8_bf16(reinterpret_cast<bf16*>(p.C) + (long long)row * p.ldc + col, acc);
+        st8_bf16(reinterpret_cast<bf16*>(p.C2) + (long long)row * p.ldc2 + col, act);
+      } else if constexpr (EPI == VDS_EPI_GATE_RES) {
+        const int b = row / p.rows_per_batch;
+        float g8[8], x8[8], o8[8];
+        ld8_bf16(p.gate + (long long)b * p.gate_stride + col, g8);
+        ld8_bf16(p.aux + (long long)row * p.ldaux + col, x8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] = bf16_round(acc[j]);                      // Linear output is bf16 in the reference
+          o8[j] = x8[j] + bf16_round(acc[j] * g8[j]);      // x + (out * gate), each op rounded to bf16
+        }
+        if (p.C != nullptr) st8_bf16(reinterpret_cast<bf16*>(p.C) + (long long)row * p.ldc + col, acc);
+        st8_bf16(reinterpret_cast<bf16*>(p.C2) + (long long)row * p.ldc2 + col, o8);
+      } else if constexpr (EPI == VDS_EPI_DGELU) {
+        float h8[8];
+        ld8_bf16(p.aux + (long long)row * p.ldaux + col, h8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= dgelu_erf(h8[j]);
+        st8_bf16(reinterpret_cast<bf16*>(p.C) + (long long)row * p.ldc + col, acc);
+      }
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
+
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int k_iters = (p.K + BK - 1) / BK;
+  const int total_tiles = m_tiles * n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % m_tiles;
+        const int rest = tile / m_tiles;
+        const int nt = rest % n_tiles;
+        const int sp = rest / n_tiles;
+        const int kb0 = sp * p.k_per_split;
+        const int kb1 = min(k_iters, kb0 + p.k_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t a_dst = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d(a_dst, &tmA, full_bar(stage), kb * BK, mt * BM);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_2d(a_dst + i * (BK * 128), &tmA, full_bar(stage), mt * BM + i * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, nt * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(b_dst + i * (BK * 128), &tmB, full_bar(stage), nt * BN + i * 64, kb * BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int rest = tile / m_tiles;
+        const int sp = rest / n_tiles;
+        const int kb0 = sp * p.k_per_split;
+        const int kb1 = min(k_iters, kb0 + p.k_per_split);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + k * 2048, BK * 128, 1024)
+                                        : umma_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + k * 2048, BK * 128, 1024)
+                                        : umma_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile % m_tiles;
+      const int nt = (tile / m_tiles) % n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = mt * BM + q * 32 + lane;
+      const uint32_t t_base = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_base + c * 32, v);
+        tmem_ld_wait();
+        epilogue_row<EPI>(p, row, nt * BN + c * 32, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    if (!A_MN) { dims[0] = a.K; dims[1] = a.M; box[0] = BK; box[1] = BM; }
+    else       { dims[0] = a.M; dims[1] = a.K; box[0] = 64; box[1] = BK; }
+    strides[0] = (uint64_t)a.lda * 2;
+    int r = encode_tmap_bf16(&tmA, a.A, 2, dims, strides, box);
+    if (r) return r;
+    if (!B_MN) { dims[0] = a.K; dims[1] = a.N; box[0] = BK; box[1] = BN; }
+    else       { dims[0] = a.N; dims[1] = a.K; box[0] = 64; box[1] = BK; }
+    strides[0] = (uint64_t)a.ldb * 2;
+    r = encode_tmap_bf16(&tmB, a.B, 2, dims, strides, box);
+    if (r) return r;
+  }
+  GemmDev p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  const int k_iters = (a.K + BK - 1) / BK;
+  int splits = (EPI == VDS_EPI_ACCUM_F32) ? (a.splits < 1 ? 1 : a.splits) : 1;
+  if (splits > k_iters) splits = k_iters;
+  p.k_per_split = (k_iters + splits - 1) / splits;
+  p.splits = (k_iters + p.k_per_split - 1) / p.k_per_split;  // every split non-empty
+  p.C = a.C; p.ldc = a.ldc; p.C2 = a.C2; p.ldc2 = a.ldc2;
+  p.bias = reinterpret_cast<const bf16*>(a.bias);
+  p.aux = reinterpret_cast<const bf16*>(a.aux); p.ldaux = a.ldaux;
+  p.gate = reinterpret_cast<const bf16*>(a.gate); p.gate_stride = a.gate_stride;
+  p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
+  p.remap_rows = a.remap_rows; p.remap_stride = a.remap_stride; p.remap_offset = a.remap_offset;
+
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return VDS_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int m_tiles = (a.M + BM - 1) / BM, n_tiles = (a.N + BN - 1) / BN;
+  const long long total = (long long)m_tiles * n_tiles * p.splits;
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  VDS_CHECK_LAUNCH("gemm");
+  return VDS_OK;
+}
+
+template <bool A_MN, bool B_MN>
+static int dispatch_epi(const vds_gemm_args& a, cudaStream_t s) {
+  switch (a.epilogue) {
+    case VDS_EPI_STORE: return launch_gemm<128, A_MN, B_MN, VDS_EPI_STORE>(a, s);
+    case VDS_EPI_ACCUM_F32: return launch_gemm<128, A_MN, B_MN, VDS_EPI_ACCUM_F32>(a, s);
+    case VDS_EPI_STORE_F32: return launch_gemm<128, A_MN, B_MN, VDS_EPI_STORE_F32>(a, s);
+    default: break;
+  }
+  if constexpr (!A_MN) {
+    switch (a.epilogue) {
+      case VDS_EPI_BIAS_GELU: if constexpr (!B_MN) return launch_gemm<128, A_MN, B_MN, VDS_EPI_BIAS_GELU>(a, s); break;
+      case VDS_EPI_GATE_RES: if constexpr (!B_MN) return launch_gemm<128, A_MN, B_MN, VDS_EPI_GATE_RES>(a, s); break;
+      case VDS_EPI_DGELU: if constexpr (B_MN) return launch_gemm<128, A_MN, B_MN, VDS_EPI_DGELU>(a, s); break;
+      default: break;
+    }
+  }
+  set_error("gemm: epilogue %d not available for a_mn=%d b_mn=%d", a.epilogue, (int)A_MN, (int)B_MN);
+  return VDS_ERR_UNSUPPORTED;
+}
+
+}  // namespace vds
+
+extern "C" int vds_gemm(const vds_gemm_args* args, void* stream) {
+  using namespace vds;
+  VDS_CHECK_ARG(args != nullptr, "gemm: null args");
+  const vds_gemm_args& a = *args;
+  VDS_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+  VDS_CHECK_ARG(a.N % 8 == 0, "gemm: N=%d must be a multiple of 8", a.N);
+  VDS_CHECK_ARG(a.lda % 8 == 0 && a.ldb % 8 == 0, "gemm: lda=%lld ldb=%lld must be multiples of 8",
+                (long long)a.lda, (long long)a.ldb);
+  VDS_CHECK_ARG(((uintptr_t)a.A & 15) == 0 && ((uintptr_t)a.B & 15) == 0, "gemm: A/B must be 16-byte aligned");
+  VDS_CHECK_ARG(a.C != nullptr || a.C2 != nullptr, "gemm: no output");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (!a.a_mn && !a.b_mn) return dispatch_epi<false, false>(a, s);
+  if (!a.a_mn && a.b_mn) return dispatch_epi<false, true>(a, s);
+  if (a.a_mn && a.b_mn) return dispatch_epi<true, true>(a, s);
+  return dispatch_epi<true, false>(a, s);
+}

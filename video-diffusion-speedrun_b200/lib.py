@@ -1,0 +1,71 @@
+"""ctypes binding of ``libvds_b200.so`` (C ABI declared in ``include/vds_b200.h``).
+
+There is deliberately NO fallback: if the shared object is missing, or a launch fails, we raise.
+"""
+import ctypes
+import os
+import subprocess
+
+from . import PKG_DIR
+
+CSRC = os.path.join(PKG_DIR, "csrc")
+SO_PATH = os.path.join(CSRC, "libvds_b200.so")
+
+i32, i64, vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
+f32 = ctypes.c_float
+
+
+class VdsError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile every CUDA source for sm_100a into ``csrc/libvds_b200.so`` (nvcc, no GPU needed)."""
+    r = subprocess.run(["make", "-j8", "-C", CSRC], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode != 0:
+        raise VdsError("building libvds_b200.so failed")
+    return SO_PATH
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("A", vp), ("B", vp), ("lda", i64), ("ldb", i64),
+        ("M", i32), ("N", i32), ("K", i32), ("a_mn", i32), ("b_mn", i32),
+        ("epilogue", i32), ("splits", i32),
+        ("C", vp), ("ldc", i64), ("C2", vp), ("ldc2", i64),
+        ("bias", vp), ("aux", vp), ("ldaux", i64),
+        ("gate", vp), ("gate_stride", i64), ("rows_per_batch", i32),
+        ("remap_rows", i32), ("remap_stride", i32), ("remap_offset", i32),
+    ]
+
+
+EPI_STORE, EPI_ACCUM_F32, EPI_BIAS_GELU, EPI_GATE_RES, EPI_DGELU, EPI_STORE_F32 = range(6)
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise VdsError(
+                f"{SO_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU / PyTorch fallback for the CUDA path)")
+        L = ctypes.CDLL(SO_PATH)
+        L.vds_last_error.restype = ctypes.c_char_p
+        L.vds_abi_version.restype = ctypes.c_int
+        L.vds_launch_count.restype = ctypes.c_int64
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise VdsError(f"{what} failed (rc={rc}): {lib().vds_last_error().decode()}")
+
+
+def launch_count():
+    return int(lib().vds_launch_count())
