@@ -1,0 +1,553 @@
+// Flash-style attention forward / backward on tcgen05 + TMEM + TMA (sm_100a), head_dim = 128,
+// non-causal, no mask (model.py:136 self-attention, model.py:157 cross-attention; autograd of both).
+//
+// Layout contract: q/k/v live inside row-major token buffers ([B, L, ld] with the head at column
+// head*128), so the "(k h d)" split of the QKV GEMM output (model.py:126) is consumed in place by
+// 4-D TMA tensor maps {d, l, head, b}; the output is written token-major [B, L, nh*128] so the
+// "b h l d -> b l (h d)" rearrange (model.py:137) disappears.
+//
+// Forward CTA = one 128-row query tile of one (b, head):
+//   warp 0  TMA producer (Q once; K/V double-buffered)       warp 1  tcgen05.mma issuer
+//   warps 2-5 softmax: thread == query row (TMEM lane), online softmax in the log2 domain,
+//             P (bf16) -> 128B-swizzled smem as the A operand of P*V, O accumulates in TMEM.
+// Backward CTA = one 128-row K/V tile of one (b, head) looping over query tiles:
+//   S^T = K Q^T, dP^T = V dO^T (TMEM) -> P^T, dS^T (smem, bf16) -> dV += P^T dO, dK += dS^T Q (TMEM),
+//   dQ tile = dS K (TMEM) reduced into an fp32 buffer with red.global.add.
+#include <cuda.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vds {
+
+constexpr int HD = 128;
+constexpr int ATT_THREADS = 192;
+constexpr int TILE_BYTES = 128 * HD * 2;  // 32 KiB: one 128 x 128 bf16 tile = two 64-wide SW128 halves
+constexpr int HALF_BYTES = TILE_BYTES / 2;
+
+// K-major operand tile (rows x 128 along the contraction): descriptor of 16-wide k-step kk
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kk) {
+  return umma_smem_desc(tile + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
+}
+// MN-major operand tile (contraction index = smem row): 16 rows per k-step
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kk) {
+  return umma_smem_desc(tile + kk * 2048, HALF_BYTES, 1024);
+}
+
+__device__ __forceinline__ void load_tile_4d(uint32_t dst, const void* tmap, uint32_t bar, int row0, int head, int b) {
+  tma_load_4d(dst, tmap, bar, 0, row0, head, b);
+  tma_load_4d(dst + HALF_BYTES, tmap, bar, 64, row0, head, b);
+}
+
+// write 8 consecutive bf16 (columns c0..c0+7, c0 % 8 == 0) of row r into a K-major SW128 tile
+__device__ __forceinline__ void st_tile8(uint8_t* tile, int r, int c0, uint4 v) {
+  *reinterpret_cast<uint4*>(tile + (c0 >> 6) * HALF_BYTES + sw128_offset(r, (c0 & 63) >> 3)) = v;
+}
+
+struct AttnFwdParams {
+  bf16* out; long long ldo;       // [B, Lq, ldo], head at column head*128
+  float* lse;                      // [B, nh, Lq], log2 domain: m + log2(l)
+  int Lq, Lk, nh;
+  float scale_log2;                // head_dim^-0.5 * log2(e)
+};
+
+constexpr int FWD_SMEM = 6 * TILE_BYTES + 256 + 1024;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw_addr);
+  const uint32_t sQ = base, sK = base + TILE_BYTES, sV = base + 3 * TILE_BYTES, sP = base + 5 * TILE_BYTES;
+  uint8_t* gP = gen + 5 * TILE_BYTES;
+  const uint32_t bars = base + 6 * TILE_BYTES;
+  const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, kv_empty = bars + 40,
+                 s_full = bars + 56, s_empty = bars + 72, p_full = bars + 88, pv_done = bars + 96,
+                 tmem_slot = bars + 104;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 6 * TILE_BYTES + 104);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.Lk + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full + 8 * s, 1);
+      mbar_init(v_full + 8 * s, 1);
+      mbar_init(kv_empty + 8 * s, 1);
+      mbar_init(s_full + 8 * s, 1);
+      mbar_init(s_empty + 8 * s, 128);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+  const uint32_t tS = tmem, tO = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      load_tile_4d(sQ, &tmQ, q_full, q0, head, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        mbar_wait(kv_empty + 8 * s, (((j >> 1) & 1) ^ 1));
+        mbar_expect_tx(k_full + 8 * s, TILE_BYTES);
+        load_tile_4d(sK + s * TILE_BYTES, &tmK, k_full + 8 * s, j * 128, head, b);
+        mbar_expect_tx(v_full + 8 * s, TILE_BYTES);
+        load_tile_4d(sV + s * TILE_BYTES, &tmV, v_full + 8 * s, j * 128, head, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, false, true);
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(k_full + 8 * s, (j >> 1) & 1);
+        mbar_wait(s_empty + 8 * s, ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16(tS + s * 128, desc_kmajor(sQ, kk), desc_kmajor(sK + s * TILE_BYTES, kk), idesc_qk, kk > 0);
+        umma_commit(s_full + 8 * s);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) issue_s(j + 1);
+        const int s = j & 1;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(v_full + 8 * s, (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16(tO, desc_kmajor(sP, kk), desc_mnmajor(sV + s * TILE_BYTES, kk), idesc_pv, (j > 0 || kk > 0));
+        umma_commit(kv_empty + 8 * s);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                 // query row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j & 1;
+      const int valid = p.Lk - j * 128;             // columns >= valid are padding
+      mbar_wait(s_full + 8 * s, (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tSj = tS + s * 128 + lane_off;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tSj + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      uint32_t pk[64];
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tSj + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (c * 32 + i < valid) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new) : 0.f;
+          float p1 = (c * 32 + i + 1 < valid) ? exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_new) : 0.f;
+          const uint32_t u = pack_bf16x2(p0, p1);
+          const float2 back = unpack_bf16x2(u);     // sum what the tensor core will actually see
+          sum += back.x + back.y;
+          pk[c * 16 + (i >> 1)] = u;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(s_empty + 8 * s);
+      const float alpha = exp2f(m_run - m_new);     // 0 on the first tile (m_run = -inf)
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);            // P smem free, O holds tiles < j
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tO + lane_off + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(tO + lane_off + c * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 16; ++g)
+        st_tile8(gP, r, g * 8, make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // epilogue: O / l -> bf16, token-major
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    const int row = q0 + r;
+    const float inv_l = 1.0f / l_run;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tO + lane_off + c * 32, v);
+      tmem_ld_wait();
+      if (row < p.Lq) {
+        bf16* dst = p.out + ((long long)b * p.Lq + row) * p.ldo + head * HD + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
+          u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
+          u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
+          u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + g * 8) = u;
+        }
+      }
+    }
+    if (row < p.Lq && p.lse != nullptr) p.lse[((long long)b * p.nh + head) * p.Lq + row] = m_run + log2f(l_run);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------ backward
+// delta[b, head, row] = sum_d dO * O   (fp32)
+__global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, long long ldo,
+                                     long long lddo, float* __restrict__ delta, int B, int L, int nh) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const long long total = (long long)B * L * nh;
+  if (gw >= total) return;
+  const int head = gw % nh;
+  const long long tok = gw / nh;           // b*L + l
+  const bf16* po = o + tok * ldo + head * HD + lane * 4;
+  const bf16* pd = d_o + tok * lddo + head * HD + lane * 4;
+  const uint2 a = *reinterpret_cast<const uint2*>(po);
+  const uint2 c = *reinterpret_cast<const uint2*>(pd);
+  const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), c0 = unpack_bf16x2(c.x), c1 = unpack_bf16x2(c.y);
+  float s = a0.x * c0.x + a0.y * c0.y + a1.x * c1.x + a1.y * c1.y;
+  s = warp_sum(s);
+  if (lane == 0) {
+    const int bb = (int)(tok / L), l = (int)(tok % L);
+    delta[((long long)bb * nh + head) * L + l] = s;
+  }
+}
+
+struct AttnBwdParams {
+  const float* lse; const float* delta;   // [B, nh, Lq]
+  float* dq_acc; long long lddq;           // fp32 [B, Lq, lddq] (+= via red)
+  bf16* dk; long long lddk;                // bf16 [B, Lk, lddk], head at head*128 (q_splits == 1)
+  bf16* dv; long long lddv;
+  float* dk_acc; float* dv_acc; long long ldkv_acc;  // fp32 accumulation targets when q_splits > 1
+  int Lq, Lk, nh, q_splits;
+  float scale_log2, scale;
+};
+
+constexpr int BWD_SMEM = 6 * TILE_BYTES + 1024 /*lse+delta*/ + 256 + 1024;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw_addr);
+  const uint32_t sK = base, sV = base + TILE_BYTES, sQ = base + 2 * TILE_BYTES, sDO = base + 3 * TILE_BYTES,
+                 sPT = base + 4 * TILE_BYTES, sDST = base + 5 * TILE_BYTES;
+  uint8_t* gPT = gen + 4 * TILE_BYTES;
+  uint8_t* gDST = gen + 5 * TILE_BYTES;
+  float* s_lse = reinterpret_cast<float*>(gen + 6 * TILE_BYTES);
+  float* s_delta = s_lse + 128;
+  const uint32_t bars = base + 6 * TILE_BYTES + 1024;
+  const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 16, sdp_full = bars + 24,
+                 pds_full = bars + 32, dq_full = bars + 40, dq_drained = bars + 48, tmem_slot = bars + 56;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 6 * TILE_BYTES + 1024 + 56);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv_tile = blockIdx.x / p.q_splits, split = blockIdx.x % p.q_splits;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int kv0 = kv_tile * 128;
+  const int n_q_all = (p.Lq + 127) / 128;
+  const int per = (n_q_all + p.q_splits - 1) / p.q_splits;
+  const int qt0 = split * per, qt1 = min(n_q_all, qt0 + per);
+  const int n_q = qt1 - qt0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    mbar_init(qdo_full, 1);
+    mbar_init(qdo_empty, 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_drained, 128);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+  const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 384, tDQ = tmem;
+
+  if (n_q > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+        load_tile_4d(sK, &tmK, kv_full, kv0, head, b);
+        load_tile_4d(sV, &tmV, kv_full, kv0, head, b);
+        for (int i = 0; i < n_q; ++i) {
+          mbar_wait(qdo_empty, (i & 1) ^ 1);
+          mbar_expect_tx(qdo_full, 2 * TILE_BYTES);
+          load_tile_4d(sQ, &tmQ, qdo_full, (qt0 + i) * 128, head, b);
+          load_tile_4d(sDO, &tmDO, qdo_full, (qt0 + i) * 128, head, b);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, false, false);
+        constexpr uint32_t idesc_kmn = umma_idesc_bf16(128, 128, false, true);
+        constexpr uint32_t idesc_mnmn = umma_idesc_bf16(128, 128, true, true);
+        mbar_wait(kv_full, 0);
+        for (int i = 0; i < n_q; ++i) {
+          mbar_wait(qdo_full, i & 1);
+          if (i > 0) mbar_wait(dq_drained, (i - 1) & 1);   // dQ(i-1) left the S^T columns
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)   // S^T = K Q^T
+            umma_bf16(tST, desc_kmajor(sK, kk), desc_kmajor(sQ, kk), idesc_kk, kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)   // dP^T = V dO^T
+            umma_bf16(tDPT, desc_kmajor(sV, kk), desc_kmajor(sDO, kk), idesc_kk, kk > 0);
+          umma_commit(sdp_full);
+          mbar_wait(pds_full, i & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)   // dV += P^T dO
+            umma_bf16(tDV, desc_kmajor(sPT, kk), desc_mnmajor(sDO, kk), idesc_kmn, (i > 0 || kk > 0));
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)   // dK += dS^T Q
+            umma_bf16(tDK, desc_kmajor(sDST, kk), desc_mnmajor(sQ, kk), idesc_kmn, (i > 0 || kk > 0));
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)   // dQ = dS K  (A = dS^T read MN-major, B = K read MN-major)
+            umma_bf16(tDQ, desc_mnmajor(sDST, kk), desc_mnmajor(sK, kk), idesc_mnmn, kk > 0);
+          umma_commit(qdo_empty);          // every operand tile of this iteration has been consumed
+          umma_commit(dq_full);
+        }
+      }
+    } else {
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;
+      const int ct = threadIdx.x - 64;     // 0..127
+      const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+      const bool kv_ok = (kv0 + r) < p.Lk;
+      const long long stat_base = ((long long)b * p.nh + head) * p.Lq;
+      for (int i = 0; i < n_q; ++i) {
+        const int q0 = (qt0 + i) * 128;
+        // stage lse / delta of this query tile (previous iteration's readers are past the named barrier below)
+        {
+          const int q = q0 + ct;
+          s_lse[ct] = q < p.Lq ? p.lse[stat_base + q] : 0.f;
+          s_delta[ct] = q < p.Lq ? p.delta[stat_base + q] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mbar_wait(sdp_full, i & 1);
+        tc_fence_after();
+        const int qvalid = p.Lq - q0;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t sv[32], dv[32];
+          tmem_ld32(tST + lane_off + c * 32, sv);
+          tmem_ld32(tDPT + lane_off + c * 32, dv);
+          tmem_ld_wait();
+          uint32_t pp[16], dd[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float pv[2], ds[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int col = c * 32 + e + u;
+              const bool ok = kv_ok && (col < qvalid);
+              const float pr = ok ? exp2f(__uint_as_float(sv[e + u]) * p.scale_log2 - s_lse[col]) : 0.f;
+              pv[u] = pr;
+              ds[u] = pr * (__uint_as_float(dv[e + u]) - s_delta[col]) * p.scale;
+            }
+            pp[e >> 1] = pack_bf16x2(pv[0], pv[1]);
+            dd[e >> 1] = pack_bf16x2(ds[0], ds[1]);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            st_tile8(gPT, r, c * 32 + g * 8, make_uint4(pp[g * 4], pp[g * 4 + 1], pp[g * 4 + 2], pp[g * 4 + 3]));
+            st_tile8(gDST, r, c * 32 + g * 8, make_uint4(dd[g * 4], dd[g * 4 + 1], dd[g * 4 + 2], dd[g * 4 + 3]));
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(pds_full);
+        // drain dQ tile: TMEM lane == query row
+        mbar_wait(dq_full, i & 1);
+        tc_fence_after();
+        const int qrow = q0 + r;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tDQ + lane_off + c * 32, v);
+          tmem_ld_wait();
+          if (qrow < p.Lq) {
+            float* dst = p.dq_acc + ((long long)b * p.Lq + qrow) * p.lddq + head * HD + c * 32;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
+                           "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
+                           "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
+                           : "memory");
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(dq_drained);
+      }
+      // dK / dV of this K/V tile (all MMAs complete: dq_full of the last iteration was waited above)
+      const int krow = kv0 + r;
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t t = (which == 0 ? tDK : tDV) + lane_off;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t + c * 32, v);
+          tmem_ld_wait();
+          if (krow < p.Lk) {
+            if (p.q_splits == 1) {
+              bf16* dst = (which == 0 ? p.dk + ((long long)b * p.Lk + krow) * p.lddk
+                                      : p.dv + ((long long)b * p.Lk + krow) * p.lddv) + head * HD + c * 32;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+                u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+                u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+                u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+                *reinterpret_cast<uint4*>(dst + g * 8) = u;
+              }
+            } else {
+              float* dst = (which == 0 ? p.dk_acc : p.dv_acc) + ((long long)b * p.Lk + krow) * p.ldkv_acc +
+                           head * HD + c * 32;
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
+                             "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
+                             "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
+                             : "memory");
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+static int make_tmap_tokens(CUtensorMap* tm, const void* ptr, long long ld, int L, int nh, int B) {
+  uint64_t dims[4] = {(uint64_t)HD, (uint64_t)L, (uint64_t)nh, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)HD * 2, (uint64_t)L * (uint64_t)ld * 2};
+  uint32_t box[4] = {64, 128, 1, 1};
+  return encode_tmap_bf16(tm, ptr, 4, dims, strides, box);
+}
+
+}  // namespace vds
+
+using namespace vds;
+
+extern "C" {
+
+/* q: [B, Lq, ldq] (head h at column h*128), k/v: [B, Lk, ldk|ldv]; out: [B, Lq, ldo]; lse: [B, nh, Lq] fp32 */
+int vds_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                 int64_t ldo, float* lse, int B, int nh, int Lq, int Lk, int head_dim, float scale, void* stream) {
+  VDS_CHECK_ARG(head_dim == HD, "attn: head_dim=%d unsupported (only 128)", head_dim);
+  VDS_CHECK_ARG(B > 0 && nh > 0 && Lq > 0 && Lk > 0, "attn: bad shape");
+  VDS_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "attn: leading dims must be multiples of 8");
+  CUtensorMap tq, tk, tv;
+  int r;
+  if ((r = make_tmap_tokens(&tq, q, ldq, Lq, nh, B))) return r;
+  if ((r = make_tmap_tokens(&tk, k, ldk, Lk, nh, B))) return r;
+  if ((r = make_tmap_tokens(&tv, v, ldv, Lk, nh, B))) return r;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
+    if (e != cudaSuccess) { set_error("attn_fwd: smem attribute: %s", cudaGetErrorString(e)); return VDS_ERR_CUDA; }
+    attr = true;
+  }
+  AttnFwdParams p;
+  p.out = (bf16*)out; p.ldo = ldo; p.lse = lse; p.Lq = Lq; p.Lk = Lk; p.nh = nh;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((Lq + 127) / 128, nh, B);
+  attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  VDS_CHECK_LAUNCH("attn_fwd");
+  return VDS_OK;
+}
+
+/* delta = rowsum(dO * O); dq_acc must be zero-initialised fp32 [B, Lq, lddq]; with q_splits > 1 dk/dv are
+ * accumulated into zero-initialised fp32 buffers dk_acc/dv_acc [B, Lk, ldkv_acc] instead of dk/dv. */
+int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
+                 int64_t ldo, const void* d_o, int64_t lddo, const float* lse, float* delta, float* dq_acc,
+                 int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, float* dk_acc, float* dv_acc,
+                 int64_t ldkv_acc, int q_splits, int B, int nh, int Lq, int Lk, int head_dim, float scale,
+                 void* stream) {
+  VDS_CHECK_ARG(head_dim == HD, "attn_bwd: head_dim=%d unsupported (only 128)", head_dim);
+  VDS_CHECK_ARG(q_splits >= 1, "attn_bwd: q_splits");
+  VDS_CHECK_ARG(q_splits == 1 ? (dk && dv) : (dk_acc && dv_acc), "attn_bwd: missing dk/dv target");
+  CUtensorMap tq, tk, tv, tdo;
+  int r;
+  if ((r = make_tmap_tokens(&tq, q, ldq, Lq, nh, B))) return r;
+  if ((r = make_tmap_tokens(&tk, k, ldk, Lk, nh, B))) return r;
+  if ((r = make_tmap_tokens(&tv, v, ldv, Lk, nh, B))) return r;
+  if ((r = make_tmap_tokens(&tdo, d_o, lddo, Lq, nh, B))) return r;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    if (e != cudaSuccess) { set_error("attn_bwd: smem attribute: %s", cudaGetErrorString(e)); return VDS_ERR_CUDA; }
+    attr = true;
+  }
+  {
+    const long long warps = (long long)B * Lq * nh;
+    attn_bwd_prep_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)o, (const bf16*)d_o, ldo, lddo, delta, B, Lq, nh);
+    VDS_CHECK_LAUNCH("attn_bwd_prep");
+  }
+  AttnBwdParams p;
+  p.lse = lse; p.delta = delta; p.dq_acc = dq_acc; p.lddq = lddq;
+  p.dk = (bf16*)dk; p.lddk = lddk; p.dv = (bf16*)dv; p.lddv = lddv;
+  p.dk_acc = dk_acc; p.dv_acc = dv_acc; p.ldkv_acc = ldkv_acc;
+  p.Lq = Lq; p.Lk = Lk; p.nh = nh; p.q_splits = q_splits;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(((Lk + 127) / 128) * q_splits, nh, B);
+  attn_bwd_kernel<<<grid, ATT_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, tdo, p);
+  VDS_CHECK_LAUNCH("attn_bwd");
+  return VDS_OK;
+}
+
+}  // extern "C"

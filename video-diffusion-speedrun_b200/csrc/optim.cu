@@ -1,0 +1,121 @@
+// Fused denoising-MSE loss (+ its gradient) and fused multi-tensor AdamW — both HBM-bound streams.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vds {
+
+// loss = mean_b mean_rest (v - out)^2 with v = bf16(x - noise)            (train.py:117,121-125)
+// d_out = 2*(out - v) / (B*per) * gscale  (bf16).  Grid (chunks, B).
+__global__ void __launch_bounds__(256) loss_kernel(const bf16* __restrict__ x, const bf16* __restrict__ noise,
+                                                   const bf16* __restrict__ out, bf16* __restrict__ d_out,
+                                                   float* __restrict__ loss_sum, float* __restrict__ loss_batch,
+                                                   long long per, int B, float gscale) {
+  const int b = blockIdx.y;
+  const long long base = (long long)b * per;
+  const float k = 2.0f * gscale / ((float)B * (float)per);
+  float acc = 0.f;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < per;
+       i += (long long)gridDim.x * blockDim.x * 8) {
+    if (i + 8 <= per) {
+      const uint4 ux = *reinterpret_cast<const uint4*>(x + base + i);
+      const uint4 un = *reinterpret_cast<const uint4*>(noise + base + i);
+      const uint4 uo = *reinterpret_cast<const uint4*>(out + base + i);
+      const uint32_t* px = &ux.x; const uint32_t* pn = &un.x; const uint32_t* po = &uo.x;
+      uint32_t g[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fx = unpack_bf16x2(px[j]), fn = unpack_bf16x2(pn[j]), fo = unpack_bf16x2(po[j]);
+        const float d0 = fo.x - bf16_round(fx.x - fn.x), d1 = fo.y - bf16_round(fx.y - fn.y);
+        acc += d0 * d0 + d1 * d1;
+        g[j] = pack_bf16x2(d0 * k, d1 * k);
+      }
+      if (d_out != nullptr) *reinterpret_cast<uint4*>(d_out + base + i) = make_uint4(g[0], g[1], g[2], g[3]);
+    } else {
+      for (long long j = i; j < per; ++j) {
+        const float d = __bfloat162float(out[base + j]) -
+                        bf16_round(__bfloat162float(x[base + j]) - __bfloat162float(noise[base + j]));
+        acc += d * d;
+        if (d_out != nullptr) d_out[base + j] = __float2bfloat16_rn(d * k);
+      }
+    }
+  }
+  __shared__ float red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(loss_sum, s / ((float)B * (float)per));
+    if (loss_batch != nullptr) atomicAdd(loss_batch + b, s / (float)per);
+  }
+}
+
+// torch.optim.AdamW(fused=True) semantics (train.py:340-344), one launch for every parameter:
+//   p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+// Chunks never straddle tensors; each chunk carries its param-group id (per-group lr / wd by value).
+struct AdamArgs {
+  float* p; const float* g; float* m; float* v; bf16* p_bf16;
+  const long long* chunk_start; const int* chunk_len; const int* chunk_group;
+  float lr[16]; float wd[16];
+  float beta1, beta2, eps, bc1, bc2_sqrt, gscale;
+};
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a) {
+  const int c = blockIdx.x;
+  const long long s = a.chunk_start[c];
+  const int n = a.chunk_len[c];
+  const int grp = a.chunk_group[c];
+  const float lr = a.lr[grp], decay = 1.0f - lr * a.wd[grp], step = lr / a.bc1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long k = s + i;
+    const float g = a.g[k] * a.gscale;
+    float p = a.p[k] * decay;
+    const float m = a.beta1 * a.m[k] + (1.0f - a.beta1) * g;
+    const float v = a.beta2 * a.v[k] + (1.0f - a.beta2) * g * g;
+    p -= step * m / (sqrtf(v) / a.bc2_sqrt + a.eps);
+    a.p[k] = p; a.m[k] = m; a.v[k] = v;
+    if (a.p_bf16 != nullptr) a.p_bf16[k] = __float2bfloat16_rn(p);
+  }
+}
+
+}  // namespace vds
+
+using namespace vds;
+
+extern "C" {
+
+int vds_loss_fwd_bwd(const void* x, const void* noise, const void* out, void* d_out, float* loss_sum,
+                     float* loss_batch, int B, int64_t per_sample, float grad_scale, void* stream) {
+  VDS_CHECK_ARG(per_sample % 8 == 0, "loss: per-sample element count must be a multiple of 8");
+  int chunks = (int)((per_sample / 8 + 255) / 256);
+  const int cap = (4 * num_sms() + B - 1) / B;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, B);
+  loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)noise, (const bf16*)out,
+                                                      (bf16*)d_out, loss_sum, loss_batch, per_sample, B, grad_scale);
+  VDS_CHECK_LAUNCH("loss");
+  return VDS_OK;
+}
+
+int vds_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const int64_t* chunk_start,
+              const int32_t* chunk_len, const int32_t* chunk_group, int n_chunks, const float* lr_host,
+              const float* wd_host, int n_groups, float beta1, float beta2, float eps, int step, float grad_scale,
+              void* stream) {
+  VDS_CHECK_ARG(n_groups >= 1 && n_groups <= 16, "adamw: 1..16 param groups supported (got %d)", n_groups);
+  VDS_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
+  if (n_chunks == 0) return VDS_OK;
+  AdamArgs a;
+  a.p = p; a.g = g; a.m = m; a.v = v; a.p_bf16 = (bf16*)p_bf16;
+  a.chunk_start = (const long long*)chunk_start; a.chunk_len = chunk_len; a.chunk_group = chunk_group;
+  for (int i = 0; i < 16; ++i) { a.lr[i] = i < n_groups ? lr_host[i] : 0.f; a.wd[i] = i < n_groups ? wd_host[i] : 0.f; }
+  a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+  a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  a.gscale = grad_scale;
+  adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(a);
+  VDS_CHECK_LAUNCH("adamw");
+  return VDS_OK;
+}
+
+}  // extern "C"

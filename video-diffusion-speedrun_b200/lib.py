@@ -44,6 +44,33 @@ class GemmArgs(ctypes.Structure):
 
 EPI_STORE, EPI_ACCUM_F32, EPI_BIAS_GELU, EPI_GATE_RES, EPI_DGELU, EPI_STORE_F32 = range(6)
 
+fp = ctypes.POINTER(ctypes.c_float)
+
+# name -> argtypes; must match include/vds_b200.h (checked by tests/test_abi.py)
+_SIGNATURES = {
+    "vds_gemm": [ctypes.POINTER(GemmArgs), vp],
+    "vds_patchify": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "vds_unpatchify": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "vds_rope_rows": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "vds_timestep_embedding": [vp, vp, i32, i32, f32, vp],
+    "vds_silu": [vp, vp, i64, vp],
+    "vds_silu_bwd": [vp, vp, vp, i64, vp],
+    "vds_rmsnorm_mod_fwd": [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, f32, vp],
+    "vds_rmsnorm_mod_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, i32, vp],
+    "vds_gate_bwd": [vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp],
+    "vds_qkv_post_fwd": [vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, vp],
+    "vds_qkv_post_bwd": [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+    "vds_colsum": [vp, vp, i64, i32, i64, vp],
+    "vds_batch_rowsum": [vp, vp, i32, i64, i32, i32, vp],
+    "vds_cast_f32_bf16": [vp, vp, i64, f32, vp],
+    "vds_accum_bf16_f32": [vp, vp, i64, i32, vp],
+    "vds_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, f32, vp],
+    "vds_attn_bwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp, i64, vp, vp,
+                     i64, i32, i32, i32, i32, i32, i32, f32, vp],
+    "vds_loss_fwd_bwd": [vp, vp, vp, vp, vp, vp, i32, i64, f32, vp],
+    "vds_adamw": [vp, vp, vp, vp, vp, vp, vp, vp, i32, fp, fp, i32, f32, f32, f32, i32, f32, vp],
+}
+
 _lib = None
 
 
@@ -58,6 +85,10 @@ def lib():
         L.vds_last_error.restype = ctypes.c_char_p
         L.vds_abi_version.restype = ctypes.c_int
         L.vds_launch_count.restype = ctypes.c_int64
+        for name, argtypes in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_int
         _lib = L
     return _lib
 

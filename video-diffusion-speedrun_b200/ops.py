@@ -64,3 +64,189 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=L.EPI_STORE, out=None, out2=N
         args.remap_rows, args.remap_stride, args.remap_offset = remap
     L.check(L.lib().vds_gemm(ctypes.byref(args), _stream()), "vds_gemm")
     return (out, out2) if out2 is not None else out
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def patchify(x, p, pt, noise=None, t=None, out=None):
+    """[B,C,T,H,W] -> [B*N, C*pt*p*p] in the reference's token / Conv3d-weight order (model.py:173-185);
+    with `noise`/`t` also forms z_t = x*(1-t) + noise*t in bf16 (train.py:115-116)."""
+    _chk_bf16(x, noise, t)
+    B, C, T, H, W = x.shape
+    assert x.is_contiguous()
+    n = (T // pt) * (H // p) * (W // p)
+    if out is None:
+        out = torch.empty((B * n, C * pt * p * p), device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().vds_patchify(_p(x), _p(noise), _p(t), _p(out), B, C, T, H, W, p, pt, _s()), "vds_patchify")
+    return out
+
+
+def unpatchify(y, B, C, T, H, W, p, pt, to_tokens=False, out=None):
+    """tokens [B*N, p*p*pt*C] -> [B,C,T,H,W] (model.py:392-401); to_tokens=True is the inverse gather."""
+    _chk_bf16(y)
+    n = (T // pt) * (H // p) * (W // p)
+    if out is None:
+        shape = (B * n, C * pt * p * p) if to_tokens else (B, C, T, H, W)
+        out = torch.empty(shape, device=y.device, dtype=torch.bfloat16)
+    assert y.is_contiguous() and out.is_contiguous()
+    L.check(L.lib().vds_unpatchify(_p(y), _p(out), B, C, T, H, W, p, pt, int(to_tokens), _s()), "vds_unpatchify")
+    return out
+
+
+def rope_rows(tcos, tsin, thw, starts, n_reg):
+    """Gather cos/sin rows [L, D] (fp32) from the persistent tables at (start_t, start_h, start_w)."""
+    Tp, Hp, Wp = thw
+    st, sh, sw = starts
+    D = tcos.shape[-1]
+    Lr = n_reg + Tp * Hp * Wp
+    assert tcos.dtype in (torch.float32, torch.bfloat16) and tcos.is_contiguous() and tsin.is_contiguous()
+    ocos = torch.empty((Lr, D), device=tcos.device, dtype=torch.float32)
+    osin = torch.empty_like(ocos)
+    L.check(L.lib().vds_rope_rows(_p(tcos), _p(tsin), int(tcos.dtype == torch.bfloat16), _p(ocos), _p(osin), Lr, D,
+                                  n_reg, Tp, Hp, Wp, st, sh, sw, tcos.shape[1], tcos.shape[2], _s()), "vds_rope_rows")
+    return ocos, osin
+
+
+def timestep_embedding(t, dim, max_period=10000.0):
+    _chk_bf16(t)
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.bfloat16)
+    L.check(L.lib().vds_timestep_embedding(_p(t), _p(out), t.shape[0], dim, float(max_period), _s()),
+            "vds_timestep_embedding")
+    return out
+
+
+def silu(x):
+    _chk_bf16(x)
+    y = torch.empty_like(x)
+    L.check(L.lib().vds_silu(_p(x), _p(y), x.numel(), _s()), "vds_silu")
+    return y
+
+
+def silu_bwd(x, dy):
+    _chk_bf16(x, dy)
+    dx = torch.empty_like(x)
+    L.check(L.lib().vds_silu_bwd(_p(x), _p(dy), _p(dx), x.numel(), _s()), "vds_silu_bwd")
+    return dx
+
+
+def rmsnorm_mod_fwd(x, B, rows_out, h, scale=None, shift=None, weight=None, in_batch_stride=None, in_row_offset=0,
+                    eps=1e-6, want_rstd=True):
+    """y = rmsnorm(x)[*w] * (1 + scale[b]) + shift[b] with the reference's bf16 rounding points."""
+    _chk_bf16(x, scale, shift, weight)
+    if in_batch_stride is None:
+        in_batch_stride = rows_out
+    y = torch.empty((B * rows_out, h), device=x.device, dtype=torch.bfloat16)
+    rstd = torch.empty((B * rows_out,), device=x.device, dtype=torch.float32) if want_rstd else None
+    ms = scale.stride(0) if scale is not None else 0
+    L.check(L.lib().vds_rmsnorm_mod_fwd(_p(x), _p(y), _p(rstd), _p(weight), _p(scale), _p(shift), ms, B, rows_out,
+                                        in_batch_stride, in_row_offset, h, eps, _s()), "vds_rmsnorm_mod_fwd")
+    return y, rstd
+
+
+def rmsnorm_mod_bwd(dy, x, rstd, B, rows_out, h, scale=None, weight=None, dx_res=None, dx=None, dscale=None,
+                    dshift=None, dweight=None, in_batch_stride=None, in_row_offset=0, dx_full_rows=False):
+    _chk_bf16(dy, x, scale, weight, dx_res)
+    if in_batch_stride is None:
+        in_batch_stride = rows_out
+    if dx is None:
+        dx = torch.empty((B * (in_batch_stride if dx_full_rows else rows_out), h), device=x.device,
+                         dtype=torch.bfloat16)
+    ms = scale.stride(0) if scale is not None else 0
+    dms = dscale.stride(0) if dscale is not None else 0
+    L.check(L.lib().vds_rmsnorm_mod_bwd(_p(dy), _p(x), _p(rstd), _p(weight), _p(scale), _p(dx_res), _p(dx),
+                                        _p(dscale), _p(dshift), _p(dweight), ms, dms, B, rows_out, in_batch_stride,
+                                        in_row_offset, int(dx_full_rows), h, _s()), "vds_rmsnorm_mod_bwd")
+    return dx
+
+
+def gate_bwd(dx, o, gate, dgate, B, rows, h):
+    """do = dx*gate[b]; dgate[b] += sum_rows dx*o."""
+    _chk_bf16(dx, o, gate)
+    d_o = torch.empty((B * rows, h), device=dx.device, dtype=torch.bfloat16)
+    L.check(L.lib().vds_gate_bwd(_p(dx), _p(o), _p(gate), _p(d_o), _p(dgate), gate.stride(0), dgate.stride(0), B, rows,
+                                 h, _s()), "vds_gate_bwd")
+    return d_o
+
+
+def qkv_post_fwd(qkv, B, Lr, h, nh, cos=None, sin=None, v0=None, v0_ld=0, lam=None):
+    _chk_bf16(qkv, v0, lam)
+    vmix = torch.empty((B * Lr, h), device=qkv.device, dtype=torch.bfloat16) if v0 is not None else None
+    L.check(L.lib().vds_qkv_post_fwd(_p(qkv), _p(cos), _p(sin), _p(v0), v0_ld, _p(vmix), _p(lam), B, Lr, h, nh, _s()),
+            "vds_qkv_post_fwd")
+    return vmix
+
+
+def qkv_post_bwd(dqkv, B, Lr, h, nh, dq_acc=None, cos=None, sin=None, qkv_pre=None, v0=None, v0_ld=0, lam=None,
+                 dlambda=None, dv0_acc=None, mode=0):
+    L.check(L.lib().vds_qkv_post_bwd(_p(dqkv), _p(dq_acc), _p(cos), _p(sin), _p(qkv_pre), _p(v0), v0_ld, _p(lam),
+                                     _p(dlambda), _p(dv0_acc), mode, B, Lr, h, nh, _s()), "vds_qkv_post_bwd")
+
+
+def colsum(x, out, rows=None, n=None):
+    """out[n] (fp32) += sum_rows x[row, n]"""
+    _chk_bf16(x)
+    rows = x.shape[0] if rows is None else rows
+    n = x.shape[1] if n is None else n
+    L.check(L.lib().vds_colsum(_p(x), _p(out), rows, n, x.stride(0), _s()), "vds_colsum")
+
+
+def batch_rowsum(x, out, B, batch_stride, rows, h):
+    L.check(L.lib().vds_batch_rowsum(_p(x), _p(out), B, batch_stride, rows, h, _s()), "vds_batch_rowsum")
+
+
+def cast_f32_bf16(x, out=None, scale=1.0):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().vds_cast_f32_bf16(_p(x), _p(out), x.numel(), scale, _s()), "vds_cast_f32_bf16")
+    return out
+
+
+def accum_bf16_f32(x, out, accumulate=True):
+    _chk_bf16(x)
+    assert out.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()
+    L.check(L.lib().vds_accum_bf16_f32(_p(x), _p(out), x.numel(), int(accumulate), _s()), "vds_accum_bf16_f32")
+
+
+def attn_fwd(q, k, v, B, nh, Lq, Lk, out=None, want_lse=True, hd=128):
+    """q/k/v: 2-D token-major views [B*L, >= nh*hd] (unit inner stride; may be column slices of a wider buffer)."""
+    _chk_bf16(q, k, v)
+    if out is None:
+        out = torch.empty((B * Lq, nh * hd), device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty((B, nh, Lq), device=q.device, dtype=torch.float32) if want_lse else None
+    L.check(L.lib().vds_attn_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0),
+                                 _p(lse), B, nh, Lq, Lk, hd, float(hd) ** -0.5, _s()), "vds_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(q, k, v, o, d_o, lse, B, nh, Lq, Lk, dq_acc, dk=None, dv=None, dk_acc=None, dv_acc=None, q_splits=1,
+             hd=128):
+    """dq_acc: zeroed fp32 [B*Lq, nh*hd]; dk/dv: bf16 2-D views (q_splits == 1) or fp32 accumulators."""
+    _chk_bf16(q, k, v, o, d_o)
+    delta = torch.empty((B, nh, Lq), device=q.device, dtype=torch.float32)
+    L.check(L.lib().vds_attn_bwd(
+        _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(d_o), d_o.stride(0),
+        _p(lse), _p(delta), _p(dq_acc), dq_acc.stride(0), _p(dk), dk.stride(0) if dk is not None else 0, _p(dv),
+        dv.stride(0) if dv is not None else 0, _p(dk_acc), _p(dv_acc),
+        dk_acc.stride(0) if dk_acc is not None else 0, q_splits, B, nh, Lq, Lk, hd, float(hd) ** -0.5, _s()),
+        "vds_attn_bwd")
+    return delta
+
+
+def loss_fwd_bwd(x, noise, out, want_grad=True, grad_scale=1.0, want_batch=False):
+    """Fused v = x - noise, MSE against `out`, and d loss / d out (train.py:117-125)."""
+    _chk_bf16(x, noise, out)
+    B = x.shape[0]
+    per = x.numel() // B
+    d_out = torch.empty_like(out) if want_grad else None
+    loss = torch.zeros((1,), device=x.device, dtype=torch.float32)
+    lb = torch.zeros((B,), device=x.device, dtype=torch.float32) if want_batch else None
+    L.check(L.lib().vds_loss_fwd_bwd(_p(x), _p(noise), _p(out), _p(d_out), _p(loss), _p(lb), B, per, grad_scale,
+                                     _s()), "vds_loss_fwd_bwd")
+    return loss, d_out, lb
