@@ -77,6 +77,79 @@ typedef struct vds_gemm_args {
 
 int vds_gemm(const vds_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------- index / elementwise
+ * All replace chains of ATen elementwise / copy kernels at the cited reference lines. */
+
+/* x[B,C,T,H,W] -> A[B*N, C*pt*p*p]; token (h' w' t'), feature ((c*pt+dt)*p+dh)*p+dw.  model.py:173-185.
+ * noise/t non-NULL: also forms z_t = x*(1-t[b]) + noise*t[b] in bf16 arithmetic.     train.py:115-116 */
+int vds_patchify(const void* x, const void* noise, const void* t, void* out, int B, int C, int T, int H, int W,
+                 int p, int pt, void* stream);
+/* tokens [B*N, p*p*pt*C] -> [B,C,T,H,W] (to_tokens=0) or the inverse gather (to_tokens=1).  model.py:392-401 */
+int vds_unpatchify(const void* src, void* dst, int B, int C, int T, int H, int W, int p, int pt, int to_tokens,
+                   void* stream);
+/* cos/sin rows [L, D] fp32 from the persistent tables [tmax,hmax,wmax,D] (fp32 or bf16) at the random start
+ * offsets; rows < n_reg are the identity rotation; rows flattened "(t h w)".           model.py:219-263 */
+int vds_rope_rows(const void* tcos, const void* tsin, int table_is_bf16, float* ocos, float* osin, int L, int D,
+                  int n_reg, int Tp, int Hp, int Wp, int st, int sh, int sw, int hmax, int wmax, void* stream);
+/* [cos(t f_i) | sin(t f_i)], bf16 out.                                                  model.py:12-22 */
+int vds_timestep_embedding(const void* t, void* out, int B, int dim, float max_period, void* stream);
+/* SiLU and its backward (nn.SiLU at model.py:90,320,340). */
+int vds_silu(const void* x, void* y, int64_t n, void* stream);
+int vds_silu_bwd(const void* x, const void* dy, void* dx, int64_t n, void* stream);
+
+/* y = bf16(bf16(bf16(x*rstd[*w]) * bf16(1+scale[b])) + shift[b]); optional row map (final norm reads rows
+ * in_row_offset.. of each sample and writes compact rows).              model.py:34-41,123,144,164,386-389 */
+int vds_rmsnorm_mod_fwd(const void* x, void* y, float* rstd, const void* weight, const void* scale,
+                        const void* shift, int64_t mod_stride, int B, int rows_per_batch_out, int in_batch_stride,
+                        int in_row_offset, int h, float eps, void* stream);
+/* backward of the above: dx (+ dx_res), dscale/dshift [B,h] (fp32, +=), dweight [h] (fp32, +=). */
+int vds_rmsnorm_mod_bwd(const void* dy, const void* x, const float* rstd, const void* weight, const void* scale,
+                        const void* dx_res, void* dx, float* dscale, float* dshift, float* dweight,
+                        int64_t mod_stride, int64_t dmod_stride, int B, int rows_per_batch_out, int in_batch_stride,
+                        int in_row_offset, int dx_full_rows, int h, void* stream);
+/* backward of x + o*gate[b]: d_o = dx*gate[b]; dgate[b] += sum_rows dx*o.               model.py:139,160,165 */
+int vds_gate_bwd(const void* dx, const void* o, const void* gate, void* d_o, float* dgate, int64_t gate_stride,
+                 int64_t dgate_stride, int B, int rows_per_batch, int h, void* stream);
+/* in place on qkv [B,L,3h]: RoPE(q), RoPE(k) (model.py:132-134,266-275); vmix = l*v + (1-l)*v0 (model.py:130). */
+int vds_qkv_post_fwd(void* qkv, const float* cos, const float* sin, const void* v0, int64_t v0_ld, void* vmix,
+                     const void* lambda, int B, int L, int h, int nh, void* stream);
+/* backward of the above, in place on dqkv (dq optionally read from the fp32 accumulation buffer). */
+int vds_qkv_post_bwd(void* dqkv, const float* dq_acc, const float* cos, const float* sin, const void* qkv_pre,
+                     const void* v0, int64_t v0_ld, const void* lambda, float* dlambda, float* dv0_acc, int mode,
+                     int B, int L, int h, int nh, void* stream);
+/* out[n] += sum_rows x[row,n] (bias gradients); out[r,:] += sum_b x[b,r,:] (register-token gradient). */
+int vds_colsum(const void* x, float* out, int64_t rows, int n, int64_t ld, void* stream);
+int vds_batch_rowsum(const void* x, float* out, int B, int64_t batch_stride, int rows, int h, void* stream);
+int vds_cast_f32_bf16(const float* x, void* y, int64_t n, float scale, void* stream);
+int vds_accum_bf16_f32(const void* x, float* y, int64_t n, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------ attention
+ * F.scaled_dot_product_attention (model.py:136 self, model.py:157 cross) and its autograd, head_dim 128,
+ * on tcgen05/TMEM with TMA producers.  q/k/v/out are token-major [B, L, ld] buffers with head i at column
+ * i*128 (so "(k h d)" / "b h l d -> b l (h d)" rearranges, model.py:126,137, need no copies).
+ * lse: [B, nh, Lq] fp32 in the log2 domain.  Backward: dq_acc is a zero-initialised fp32 buffer reduced
+ * into with red.global.add; with q_splits > 1 dk/dv are reduced into fp32 dk_acc/dv_acc instead. */
+int vds_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                 int64_t ldo, float* lse, int B, int nh, int Lq, int Lk, int head_dim, float scale, void* stream);
+int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
+                 int64_t ldo, const void* d_o, int64_t lddo, const float* lse, float* delta, float* dq_acc,
+                 int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, float* dk_acc, float* dv_acc,
+                 int64_t ldkv_acc, int q_splits, int B, int nh, int Lq, int Lk, int head_dim, float scale,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------ loss / optimizer
+ * loss_sum += mean_b mean_rest (bf16(x-noise) - out)^2 ; d_out = 2(out - v)/(B*per) * grad_scale
+ * (* grad_scale_dev[0] if non-NULL: the upstream autograd scalar, read on the device).  train.py:117-125 */
+int vds_loss_fwd_bwd(const void* x, const void* noise, const void* out, void* d_out, float* loss_sum,
+                     float* loss_batch, int B, int64_t per_sample, float grad_scale, const float* grad_scale_dev,
+                     void* stream);
+/* torch.optim.AdamW(fused=True) math over flat fp32 p/g/m/v with a chunk table (chunks never straddle tensors;
+ * chunk_group indexes the host arrays lr/wd), optional bf16 copy of the updated parameters.  train.py:340-344,433 */
+int vds_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const int64_t* chunk_start,
+              const int32_t* chunk_len, const int32_t* chunk_group, int n_chunks, const float* lr_host,
+              const float* wd_host, int n_groups, float beta1, float beta2, float eps, int step, float grad_scale,
+              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

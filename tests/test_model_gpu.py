@@ -1,0 +1,120 @@
+"""End-to-end parity of the CUDA DiT train step against the oracle (and the reference's golden vectors).
+
+Tolerances are the north-star's: loss relative error <= 1e-2, per-tensor gradient cosine >= 0.999."""
+import pytest
+import torch
+
+from helpers import build_model, cos_sim, golden_case, params_of
+from oracle import dit_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-2
+GRAD_COS = 0.999
+
+
+def _cuda_step(model, latent, noise, context, t, seed, fused):
+    from vds_b200 import train
+    model.zero_grad(set_to_none=True)
+    torch.manual_seed(seed)
+    if fused:
+        loss, _ = train.forward(model, latent, context, t=t, noise=noise)
+        out = None
+    else:
+        tr = t.reshape(-1, 1, 1, 1, 1)
+        z_t = latent * (1 - tr) + noise * tr
+        out = model(z_t, context, t)
+        loss = ((latent - noise).float() - out.float()).pow(2).mean(dim=(1, 2, 3, 4)).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss.item(), out, {n: p.grad for n, p in model.named_parameters()}
+
+
+def _oracle_step(model, cfg, latent, noise, context, t, seed, thw, dtype, dev):
+    P = params_of(model, device=dev, dtype=dtype, requires_grad=True)
+    torch.manual_seed(seed)
+    starts = O.draw_rope_starts(thw)
+    loss, out = O.train_loss(P, cfg, latent.to(dev, dtype), context.to(dev, dtype), t.to(dev, dtype),
+                             noise.to(dev, dtype), rope_starts=starts)
+    loss.backward()
+    return loss.item(), out.detach(), {n: p.grad for n, p in P.items()}
+
+
+def _compare(tag, loss, grads, ref_loss, ref_grads, min_cos=GRAD_COS):
+    assert abs(loss - ref_loss) <= LOSS_RTOL * abs(ref_loss), f"{tag}: loss {loss} vs {ref_loss}"
+    worst = (1.0, None)
+    for n, rg in ref_grads.items():
+        g = grads[n]
+        if rg is None:
+            assert g is None or g.abs().max().item() == 0, n
+            continue
+        assert g is not None, f"{tag}: missing grad {n}"
+        c = cos_sim(g, rg)
+        if c < worst[0]:
+            worst = (c, n)
+        assert c >= min_cos, f"{tag}: grad cosine {c:.5f} for {n}"
+    print(f"{tag}: loss {loss:.6f} vs {ref_loss:.6f}; worst grad cosine {worst[0]:.5f} ({worst[1]})")
+
+
+@pytest.mark.parametrize("name", ["tiny_nobias", "tiny_bias"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_golden_case_vs_reference_and_oracle(cuda_dev, name, fused):
+    fx, cfg, model, (latent, noise, context, t) = golden_case(name)
+    model = model.to(cuda_dev)
+    latent, noise, context, t = [a.to(cuda_dev) for a in (latent, noise, context, t)]
+    loss, out, grads = _cuda_step(model, latent, noise, context, t, fx["seeds"]["rope"], fused)
+    # (1) against the golden vectors of the imported reference (fp32 CPU)
+    assert abs(loss - fx["loss"]) <= LOSS_RTOL * abs(fx["loss"])
+    if out is not None:
+        ref_out = fx["out"].to(cuda_dev)
+        assert (out.float() - ref_out).abs().max().item() <= 3e-2 * ref_out.abs().max().item()
+    for n, g in fx["grads"].items():
+        if g is None:
+            assert grads[n] is None or grads[n].abs().max().item() == 0
+            continue
+        got = grads[n].float().flatten().cpu()
+        assert abs(got.norm().item() - g["norm"]) <= 3e-2 * g["norm"], n
+        assert cos_sim(got[g["idx"]], g["val"]) >= 0.995, n
+    # (2) against the oracle, full tensors, fp32 on the GPU
+    thw = tuple(d // 2 for d in fx["latent_thw"])
+    rl, ro, rg = _oracle_step(model, cfg, latent, noise, context, t, fx["seeds"]["rope"], thw, torch.float32, cuda_dev)
+    _compare(f"{name}/fused={fused}", loss, grads, rl, rg)
+
+
+@pytest.mark.parametrize("train_bias", [False, True])
+def test_debug_width_vs_oracle(cuda_dev, train_bias):
+    """Debug DiT width (512, 4 heads x 128, cross-attn 4096) at reduced depth, S_small shape."""
+    cfg = dict(in_channels=16, patch_size=2, time_patch_size=2, hidden_size=512, depth=3, num_heads=4,
+               mlp_ratio=4.0, cross_attn_input_size=4096, residual_v=True, train_bias_and_rms=train_bias,
+               use_rope=True)
+    model = build_model(cfg, 0, 1).to(cuda_dev)
+    with torch.no_grad():
+        for n, p in model.named_parameters():   # train.py:247-251: 2-D params *= 0.1
+            if p.dim() == 2:
+                p.mul_(0.1)
+        for n, p in model.named_parameters():
+            if any(z in n for z in O.ZERO_INIT):
+                p.mul_(10.0)
+    latent, noise, context, t = [a.to(cuda_dev) for a in O.make_inputs(cfg, 2, (4, 32, 32), 512, 4096, 5)]
+    loss, _, grads = _cuda_step(model, latent, noise, context, t, 77, fused=True)
+    rl, _, rg = _oracle_step(model, cfg, latent, noise, context, t, 77, (2, 16, 16), torch.float32, cuda_dev)
+    _compare(f"debug512 bias={train_bias} vs fp32 oracle", loss, grads, rl, rg)
+    # the reference's own eager bf16 numerics (bf16 params + activations) for context
+    bl, _, bg = _oracle_step(model, cfg, latent, noise, context, t, 77, (2, 16, 16), torch.bfloat16, cuda_dev)
+    _compare("torch-bf16 eager vs fp32 oracle (context)", bl, bg, rl, rg, min_cos=0.98)
+
+
+def test_forward_only_and_eval(cuda_dev):
+    fx, cfg, model, (latent, noise, context, t) = golden_case("tiny_nobias")
+    model = model.to(cuda_dev, torch.bfloat16).eval()   # sample.py:63 style: bf16 module incl. bf16 rope tables
+    latent, context, t = latent.to(cuda_dev), context.to(cuda_dev), t.to(cuda_dev)
+    with torch.no_grad():
+        torch.manual_seed(3)
+        out = model(latent, context, t)
+        P = params_of(model, device=cuda_dev, dtype=torch.bfloat16)
+        torch.manual_seed(3)
+        starts = O.draw_rope_starts(tuple(d // 2 for d in fx["latent_thw"]))
+        ref = O.dit_forward({k: v.float() for k, v in P.items()}, cfg, latent.float(), context.float(), t.float(),
+                            rope_starts=starts, table_dtype=torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and out.shape == latent.shape
+    assert (out.float() - ref).abs().max().item() <= 3e-2 * ref.abs().max().item()

@@ -1,0 +1,106 @@
+"""Pins the oracle restatement (oracle/dit_oracle.py) against golden vectors produced by the imported
+reference (tests/golden/*.pt, generator: oracle/gen_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import cos_sim, golden_case, load_golden, params_of
+from oracle import dit_oracle as O
+
+
+@pytest.mark.parametrize("name", ["tiny_nobias", "tiny_bias"])
+def test_oracle_matches_reference_golden(name):
+    fx, cfg, model, (latent, noise, context, t) = golden_case(name)
+    P = params_of(model, requires_grad=True)
+    for n, (s, a) in fx["param_checksum"].items():
+        assert abs(P[n].double().sum().item() - s) <= 1e-9 * max(1.0, abs(s)), n
+        assert abs(P[n].double().abs().sum().item() - a) <= 1e-9 * max(1.0, a), n
+    torch.manual_seed(fx["seeds"]["rope"])
+    thw = tuple(d // 2 for d in fx["latent_thw"])
+    starts = O.draw_rope_starts(thw)
+    assert tuple(starts) == tuple(fx["rope_starts"])
+    loss, out = O.train_loss(P, cfg, latent.float(), context.float(), t.float(), noise.float(), rope_starts=starts)
+    loss.backward()
+    assert abs(loss.item() - fx["loss"]) <= 1e-5 * abs(fx["loss"])
+    assert (out - fx["out"]).abs().max().item() <= 1e-4 * fx["out"].abs().max().item()
+    for n, g in fx["grads"].items():
+        if g is None:
+            assert P[n].grad is None or P[n].grad.abs().max().item() == 0
+            continue
+        got = P[n].grad.flatten()
+        assert tuple(P[n].shape) == g["shape"]
+        assert abs(got.norm().item() - g["norm"]) <= 1e-3 * g["norm"] + 1e-12, n
+        assert cos_sim(got[g["idx"]], g["val"]) > 0.99999, n
+
+
+def test_oracle_mup_and_adamw_match_reference_golden():
+    fx, cfg, model, (latent, noise, context, t) = golden_case("tiny_bias")
+    shapes = {n: tuple(p.shape) for n, p in model.named_parameters()}
+    settings = O.mup_settings(shapes, 2 ** -7, 1e-1, ["patch_proj", "context_kv", "positional_embedding"])
+    for n, (lr, wd) in fx["mup"].items():
+        assert settings[n][0] == pytest.approx(lr, rel=1e-12) and settings[n][1] == pytest.approx(wd, rel=1e-12), n
+    assert len({v for v in settings.values()}) == fx["n_groups"]
+    # mirror module's get_mup_setup gives the same groups
+    groups, st = model.get_mup_setup(2 ** -7, 1e-1, ["patch_proj", "context_kv", "positional_embedding"])
+    assert len(groups) == fx["n_groups"]
+    assert {n: (s["lr"], s["wd"]) for n, s in st.items()} == fx["mup"]
+    # two AdamW steps with the golden case's gradient
+    P = params_of(model, requires_grad=True)
+    loss, _ = O.train_loss(P, cfg, latent.float(), context.float(), t.float(), noise.float(),
+                           rope_starts=fx["rope_starts"])
+    loss.backward()
+    for n, p in P.items():
+        if p.grad is None:
+            continue
+        lr, wd = settings[n]
+        q, m, v = p.detach(), torch.zeros_like(p), torch.zeros_like(p)
+        for step in (1, 2):
+            q, m, v = O.adamw_step(q, p.grad, m, v, step, lr, wd)
+        g = fx["adamw_after_2_steps"][n]
+        got = q.flatten()[g["idx"]]
+        assert torch.allclose(got, g["val"], rtol=2e-5, atol=1e-7), n
+
+
+def test_index_maps_match_reference_golden():
+    fx = load_golden("index_maps")
+    B, C, T, H, W = fx["x_shape"]
+    x = (np.arange(B * C * T * H * W) % 253).astype(np.int16).reshape(B, C, T, H, W)
+    assert np.array_equal(O.patchify_np(x, 2, 2), fx["patches"].numpy())
+    y = (np.arange(int(np.prod(fx["y_shape"]))) % 251).astype(np.int16).reshape(fx["y_shape"])
+    assert np.array_equal(O.unpatchify_np(y, C, T, H, W, 2, 2), fx["unpatch"].numpy())
+    # closed-form index helpers agree with the gather formulation
+    tok = O.patch_token_index(T // 2, H // 2, W // 2)
+    assert tok[1, 2, 3] == (2 * (W // 2) + 3) * (T // 2) + 1
+    assert O.patch_feature_index(C, 2, 2)[3, 1, 0, 1] == ((3 * 2 + 1) * 2 + 0) * 2 + 1
+    assert O.unpatch_feature_index(C, 2, 2)[1, 0, 1, 5] == ((1 * 2 + 0) * 2 + 1) * C + 5
+    cos, sin = O.rope_tables_rows(fx["rope_dim"], fx["rope_thw"], fx["rope_starts"], "cpu")
+    assert torch.allclose(cos[0, 0], fx["rope_cos"], atol=1e-6) and torch.allclose(sin[0, 0], fx["rope_sin"], atol=1e-6)
+    Tp, Hp, Wp = fx["rope_thw"]
+    assert O.rope_row_position(Wp * Hp + Wp + 1, Tp, Hp, Wp) == (1, 1, 1)
+
+
+def test_oracle_against_live_reference_if_present():
+    """Extra pin in the build container: a fresh seed against the imported reference itself."""
+    ref_path = "/root/reference/model.py"
+    if not os.path.exists(ref_path):
+        pytest.skip("reference not mounted (GPU box)")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_model_live", ref_path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    cfg = dict(in_channels=16, patch_size=2, time_patch_size=2, hidden_size=128, depth=2, num_heads=2, mlp_ratio=4.0,
+               cross_attn_input_size=32, residual_v=True, train_bias_and_rms=True, use_rope=True)
+    torch.manual_seed(11)
+    m = ref.DiT(**cfg)
+    sd = O.randomise_zero_init({k: v.clone() for k, v in m.state_dict().items() if "freqs_hwt" not in k}, seed=3)
+    m.load_state_dict(sd, strict=False)
+    latent, noise, context, t = [a.float() for a in O.make_inputs(cfg, 2, (2, 4, 6), 8, 32, 9)]
+    torch.manual_seed(77)
+    tr = t.reshape(2, 1, 1, 1, 1)
+    out = m(latent * (1 - tr) + noise * tr, context, t)
+    torch.manual_seed(77)
+    P = {k: v for k, v in sd.items()}
+    o_out = O.dit_forward(P, cfg, latent * (1 - tr) + noise * tr, context, t)
+    assert (out - o_out).abs().max().item() < 1e-5

@@ -9,8 +9,10 @@ namespace vds {
 __global__ void __launch_bounds__(256) loss_kernel(const bf16* __restrict__ x, const bf16* __restrict__ noise,
                                                    const bf16* __restrict__ out, bf16* __restrict__ d_out,
                                                    float* __restrict__ loss_sum, float* __restrict__ loss_batch,
-                                                   long long per, int B, float gscale) {
+                                                   long long per, int B, float gscale,
+                                                   const float* __restrict__ gscale_dev) {
   const int b = blockIdx.y;
+  if (gscale_dev != nullptr) gscale *= *gscale_dev;
   const long long base = (long long)b * per;
   const float k = 2.0f * gscale / ((float)B * (float)per);
   float acc = 0.f;
@@ -46,7 +48,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const bf16* __restrict__ x, c
   if (threadIdx.x == 0) {
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += red[w];
-    atomicAdd(loss_sum, s / ((float)B * (float)per));
+    if (loss_sum != nullptr) atomicAdd(loss_sum, s / ((float)B * (float)per));
     if (loss_batch != nullptr) atomicAdd(loss_batch + b, s / (float)per);
   }
 }
@@ -85,7 +87,8 @@ using namespace vds;
 extern "C" {
 
 int vds_loss_fwd_bwd(const void* x, const void* noise, const void* out, void* d_out, float* loss_sum,
-                     float* loss_batch, int B, int64_t per_sample, float grad_scale, void* stream) {
+                     float* loss_batch, int B, int64_t per_sample, float grad_scale, const float* grad_scale_dev,
+                     void* stream) {
   VDS_CHECK_ARG(per_sample % 8 == 0, "loss: per-sample element count must be a multiple of 8");
   int chunks = (int)((per_sample / 8 + 255) / 256);
   const int cap = (4 * num_sms() + B - 1) / B;
@@ -93,7 +96,8 @@ int vds_loss_fwd_bwd(const void* x, const void* noise, const void* out, void* d_
   if (chunks < 1) chunks = 1;
   dim3 grid(chunks, B);
   loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)noise, (const bf16*)out,
-                                                      (bf16*)d_out, loss_sum, loss_batch, per_sample, B, grad_scale);
+                                                      (bf16*)d_out, loss_sum, loss_batch, per_sample, B, grad_scale,
+                                                      grad_scale_dev);
   VDS_CHECK_LAUNCH("loss");
   return VDS_OK;
 }

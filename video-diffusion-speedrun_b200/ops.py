@@ -239,14 +239,17 @@ def attn_bwd(q, k, v, o, d_o, lse, B, nh, Lq, Lk, dq_acc, dk=None, dv=None, dk_a
     return delta
 
 
-def loss_fwd_bwd(x, noise, out, want_grad=True, grad_scale=1.0, want_batch=False):
+def loss_fwd_bwd(x, noise, out, want_grad=True, grad_scale=1.0, want_batch=False, want_loss=True,
+                 grad_scale_dev=None):
     """Fused v = x - noise, MSE against `out`, and d loss / d out (train.py:117-125)."""
     _chk_bf16(x, noise, out)
     B = x.shape[0]
     per = x.numel() // B
     d_out = torch.empty_like(out) if want_grad else None
-    loss = torch.zeros((1,), device=x.device, dtype=torch.float32)
+    loss = torch.zeros((1,), device=x.device, dtype=torch.float32) if want_loss else None
     lb = torch.zeros((B,), device=x.device, dtype=torch.float32) if want_batch else None
+    if grad_scale_dev is not None:
+        assert grad_scale_dev.dtype == torch.float32 and grad_scale_dev.is_cuda
     L.check(L.lib().vds_loss_fwd_bwd(_p(x), _p(noise), _p(out), _p(d_out), _p(loss), _p(lb), B, per, grad_scale,
-                                     _s()), "vds_loss_fwd_bwd")
+                                     _p(grad_scale_dev), _s()), "vds_loss_fwd_bwd")
     return loss, d_out, lb
