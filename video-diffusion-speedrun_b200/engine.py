@@ -18,9 +18,14 @@ N_REG = 16  # register tokens (model.py:316,362)
 class ParamView:
     """bf16 compute views of the parameters, keyed by the reference state_dict names."""
 
-    def __init__(self, named, depth):
+    def __init__(self, named, depth, flat=None):
         self.p = named
         self.depth = depth
+        self.flat = flat  # shard.FlatShards: per-group "parameters gathered" events to wait on
+
+    def wait_group(self, g):
+        if self.flat is not None:
+            self.flat.wait_group(g)
 
     def get(self, name):
         return self.p.get(name)
@@ -81,6 +86,7 @@ def forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise=
     c.shape = (B, C, T, H, W)
     c.dims = (N, Lr, h, nh, hd)
 
+    P.wait_group(depth)  # root group (patch embed, time embed, final head)
     # ---- patch embed (+ register tokens) : a2, a3
     A = ops.patchify(x, p, pt, noise=noise, t=t_bf if noise is not None else None)
     X = torch.empty((B * Lr, h), device=dev, dtype=torch.bfloat16)
@@ -105,6 +111,7 @@ def forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise=
     for i in range(depth):
         pre = f"blocks.{i}."
         s = Ctx()
+        P.wait_group(i)
         mod = ops.gemm(sc, P[pre + "adaLN_modulation.1.weight"], bias=P[pre + "adaLN_modulation.1.bias"])
         shift_sa, scale_sa, gate_sa, shift_ca, scale_ca, gate_ca, shift_mlp, scale_mlp, gate_mlp = _chunks(mod, h)
         # self attention

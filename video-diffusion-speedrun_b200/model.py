@@ -194,7 +194,7 @@ class DiT(nn.Module):
     def _param_view(self):
         """bf16 compute parameters: views into the gathered flat buffers when sharded, else (cast) copies."""
         if self._flat is not None:
-            return engine.ParamView(self._flat.compute_params(), self.depth)
+            return engine.ParamView(self._flat.compute_params(), self.depth, self._flat)
         return engine.ParamView(engine.bf16_params(self), self.depth)
 
     # ------------------------------------------------------------------------------------------
@@ -245,6 +245,9 @@ class DiT(nn.Module):
                 final_optimizer_settings[n] = {"lr": lr_value, "wd": per_layer_weight_decay_value,
                                                "shape": status["shape"]}
         return [v for v in param_groups.values()], final_optimizer_settings
+
+
+from .shard import apply_fsdp, get_device_mesh  # noqa: E402,F401  (model.py:475-542 surface)
 
 
 def get_module(module, access_string):

@@ -6,6 +6,11 @@ import torch
 from . import lib as L
 
 
+# bench.py hook: PROFILE["attn_bwd_self"] = [] makes attn_bwd record (start, end) CUDA events on the launch
+# stream around every self-attention backward launch (the dominant kernel of the step).
+PROFILE = {}
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -230,12 +235,19 @@ def attn_bwd(q, k, v, o, d_o, lse, B, nh, Lq, Lk, dq_acc, dk=None, dv=None, dk_a
     """dq_acc: zeroed fp32 [B*Lq, nh*hd]; dk/dv: bf16 2-D views (q_splits == 1) or fp32 accumulators."""
     _chk_bf16(q, k, v, o, d_o)
     delta = torch.empty((B, nh, Lq), device=q.device, dtype=torch.float32)
+    prof = PROFILE.get("attn_bwd_self") if Lq == Lk else None
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.check(L.lib().vds_attn_bwd(
         _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(d_o), d_o.stride(0),
         _p(lse), _p(delta), _p(dq_acc), dq_acc.stride(0), _p(dk), dk.stride(0) if dk is not None else 0, _p(dv),
         dv.stride(0) if dv is not None else 0, _p(dk_acc), _p(dv_acc),
         dk_acc.stride(0) if dk_acc is not None else 0, q_splits, B, nh, Lq, Lk, hd, float(hd) ** -0.5, _s()),
         "vds_attn_bwd")
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1))
     return delta
 
 

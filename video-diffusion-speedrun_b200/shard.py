@@ -1,0 +1,298 @@
+"""Own parameter sharding that replaces the reference's FSDP2 wrap (``apply_fsdp``, /root/reference/model.py:512-542).
+
+Same grouping as the reference (one group per DiTBlock + one root group, model.py:523-541), same mixed
+precision (bf16 parameter all-gather, fp32 gradient reduce-scatter averaged over ranks, train.py:323-325),
+but laid out for one flat buffer per kind so that every collective is ONE NCCL call with no copy-in/out:
+
+  master  fp32 [sum_g S_g]      this rank's shard of every group (+ Adam m, v alongside, see optim.py)
+  shard16 bf16 [sum_g S_g]      bf16 image of the master shard (written by the fused AdamW kernel)
+  full16  bf16 [sum_g W*S_g]    gathered compute parameters; kernels read shaped views of this
+  gfull   fp32 [sum_g W*S_g]    gradient accumulation target of the wgrad GEMM epilogues
+  gshard  fp32 [sum_g S_g]      reduce-scattered (averaged) gradients  (== gfull when W == 1)
+
+Parameters stay gathered from one optimizer step to the next (result-identical to FSDP2's
+reshard/re-gather, half the all-gather traffic; 180 GB of HBM makes this free).  All-gathers run on a
+side stream right after the optimizer step, block 0 first, and the forward waits per group; the
+reduce-scatter of block i runs on the side stream while block i-1 is still in backward.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+ALIGN = 8  # elements: keeps every bf16 parameter view 16-byte aligned (TMA requirement)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Layout:
+    """Pure-python layout math (device-free; unit-tested on CPU)."""
+
+    def __init__(self, named_shapes, depth, world):
+        self.world = world
+        groups = [[] for _ in range(depth + 1)]  # depth blocks + root (last)
+        for n, shape in named_shapes:
+            if n.startswith("blocks."):
+                groups[int(n.split(".")[1])].append((n, tuple(shape)))
+            else:
+                groups[depth].append((n, tuple(shape)))
+        self.groups = groups
+        self.param = {}  # name -> (group, offset_in_group, numel, shape)
+        self.group_numel = []  # padded, multiple of ALIGN*world
+        for g, plist in enumerate(groups):
+            off = 0
+            for n, shape in plist:
+                numel = 1
+                for s in shape:
+                    numel *= s
+                self.param[n] = (g, off, numel, shape)
+                off = _round_up(off + numel, ALIGN)
+            self.group_numel.append(_round_up(max(off, ALIGN), ALIGN * world))
+        self.shard_numel = [n // world for n in self.group_numel]
+        self.full_base = [0]
+        self.shard_base = [0]
+        for g in range(len(groups)):
+            self.full_base.append(self.full_base[-1] + self.group_numel[g])
+            self.shard_base.append(self.shard_base[-1] + self.shard_numel[g])
+        self.full_total = self.full_base[-1]
+        self.shard_total = self.shard_base[-1]
+
+    def full_range(self, name):
+        g, off, numel, _ = self.param[name]
+        return self.full_base[g] + off, numel
+
+    def shard_range(self, name, rank):
+        """(start in this rank's shard space, start inside the parameter, length) of the part rank owns."""
+        g, off, numel, _ = self.param[name]
+        S = self.shard_numel[g]
+        lo, hi = max(off, rank * S), min(off + numel, (rank + 1) * S)
+        if hi <= lo:
+            return self.shard_base[g], 0, 0
+        return self.shard_base[g] + lo - rank * S, lo - off, hi - lo
+
+    def adam_chunks(self, rank, group_of, chunk=4096):
+        """Chunk table over this rank's shard space: lists (start, len, group id); chunks never straddle tensors."""
+        starts, lens, gids = [], [], []
+        for n in self.param:
+            s, _, ln = self.shard_range(n, rank)
+            gid = group_of.get(n)
+            if gid is None:
+                continue
+            for c in range(0, ln, chunk):
+                starts.append(s + c)
+                lens.append(min(chunk, ln - c))
+                gids.append(gid)
+        return starts, lens, gids
+
+
+class FlatShards:
+    def __init__(self, model, param_dtype=torch.bfloat16, reduce_dtype=torch.float32, process_group=None,
+                 device=None):
+        assert param_dtype == torch.bfloat16 and reduce_dtype == torch.float32, \
+            "the CUDA path computes in bf16 and reduces gradients in fp32 (train.py:323-325)"
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        self.backend = dist.get_backend(process_group) if dist.is_initialized() else None
+        named = [(n, p) for n, p in model.named_parameters()]
+        if device is None:
+            device = named[0][1].device
+        self.device = torch.device(device)
+        self.depth = model.depth
+        self.layout = Layout([(n, p.shape) for n, p in named], model.depth, self.world)
+        lay = self.layout
+        f32 = dict(device=self.device, dtype=torch.float32)
+        b16 = dict(device=self.device, dtype=torch.bfloat16)
+        self.master = torch.zeros(lay.shard_total, **f32)
+        self.shard16 = torch.zeros(lay.shard_total, **b16)
+        self.full16 = torch.zeros(lay.full_total, **b16)
+        self.gfull = torch.zeros(lay.full_total, **f32)
+        self.gshard = self.gfull if self.world == 1 else torch.zeros(lay.shard_total, **f32)
+        # move the module's values into the master shard; re-point the module's Parameters at it
+        self.params = {}
+        for n, p in named:
+            s, po, ln = lay.shard_range(n, self.rank)
+            src = p.detach().to(device=self.device, dtype=torch.float32).reshape(-1)
+            self.master[s:s + ln].copy_(src[po:po + ln])
+            view = self.master[s:s + ln]
+            if self.world == 1:
+                view = view.view(p.shape)
+            newp = torch.nn.Parameter(view, requires_grad=p.requires_grad)
+            self._set_param(model, n, newp)
+            self.params[n] = newp
+        model._full_shapes = {n: lay.param[n][3] for n in lay.param}
+        self._pview = {}
+        self.grad_views = {}
+        for n in lay.param:
+            b, numel = lay.full_range(n)
+            shape = lay.param[n][3]
+            self._pview[n] = self.full16[b:b + numel].view(shape)
+            self.grad_views[n] = self.gfull[b:b + numel].view(shape)
+        self._seen_version = -1
+        self.use_cuda = self.device.type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1) if self.use_cuda else None
+        self.ag_events = [None] * (self.depth + 1)
+        self.rs_events = []
+        self._fresh = False
+        self.refresh_from_master()
+
+    @staticmethod
+    def _set_param(model, name, newp):
+        mod = model
+        parts = name.split(".")
+        for a in parts[:-1]:
+            mod = getattr(mod, a)
+        mod._parameters[parts[-1]] = newp
+
+    # ------------------------------------------------------------------------------ collectives (plumbing)
+    def _all_gather(self, out, inp):
+        if self.world == 1:
+            if out.data_ptr() != inp.data_ptr():
+                out.copy_(inp)
+            return
+        if self.backend == "gloo":  # CPU tests
+            parts = [torch.empty_like(inp) for _ in range(self.world)]
+            dist.all_gather(parts, inp, group=self.pg)
+            out.copy_(torch.cat(parts))
+        else:
+            dist.all_gather_into_tensor(out, inp, group=self.pg)
+
+    def _reduce_scatter_avg(self, out, inp):
+        if self.world == 1:
+            return
+        if self.backend == "gloo":
+            tmp = inp.clone()
+            dist.all_reduce(tmp, group=self.pg)
+            S = out.numel()
+            out.copy_(tmp[self.rank * S:(self.rank + 1) * S] / self.world)
+        else:
+            dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.AVG, group=self.pg)
+
+    def _group_slices(self, g):
+        lay = self.layout
+        fb, sb = lay.full_base[g], lay.shard_base[g]
+        return slice(fb, fb + lay.group_numel[g]), slice(sb, sb + lay.shard_numel[g])
+
+    # ------------------------------------------------------------------------------ parameters
+    def refresh_from_master(self):
+        """master (fp32 shard) -> bf16 shard -> all-gather (used at start-up, and whenever an optimizer other
+        than ours wrote the master parameters)."""
+        if self.use_cuda:
+            ops.cast_f32_bf16(self.master, out=self.shard16)
+        else:
+            self.shard16.copy_(self.master)
+        self.gather_params()
+        self._seen_version = self.master._version
+
+    def gather_params(self):
+        """All-gather every group's bf16 shard on the side stream (root group first, then block 0, 1, ...)."""
+        order = [self.depth] + list(range(self.depth))
+        if not self.use_cuda:
+            for g in order:
+                fs, ss = self._group_slices(g)
+                self._all_gather(self.full16[fs], self.shard16[ss])
+            return
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ready)
+            for g in order:
+                fs, ss = self._group_slices(g)
+                self._all_gather(self.full16[fs], self.shard16[ss])
+                ev = torch.cuda.Event()
+                ev.record(self.comm_stream)
+                self.ag_events[g] = ev
+
+    def compute_params(self):
+        if self.master._version != self._seen_version:
+            self.refresh_from_master()
+        return self._pview
+
+    def wait_group(self, g):
+        """Called by the engine before it first touches group g's parameters (g == depth: root)."""
+        ev = self.ag_events[g]
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+            self.ag_events[g] = None
+
+    # ------------------------------------------------------------------------------ gradients
+    def begin_backward(self):
+        first = next(iter(self.params.values()))
+        self._accumulate = first.grad is not None
+        if self._accumulate and self.world > 1:
+            raise NotImplementedError("gradient accumulation over several backward passes needs world_size 1")
+        if not self._accumulate:
+            self.gfull.zero_()
+        self.rs_events = []
+
+    def _reduce_group(self, g):
+        if self.world == 1:
+            return
+        fs, ss = self._group_slices(g)
+        if not self.use_cuda:
+            self._reduce_scatter_avg(self.gshard[ss], self.gfull[fs])
+            return
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(done)
+            self._reduce_scatter_avg(self.gshard[ss], self.gfull[fs])
+            ev = torch.cuda.Event()
+            ev.record(self.comm_stream)
+            self.rs_events.append(ev)
+
+    def block_backward_done(self, i):
+        self._reduce_group(i)
+
+    def end_backward(self):
+        self._reduce_group(self.depth)
+        if self.use_cuda:
+            for ev in self.rs_events:
+                torch.cuda.current_stream().wait_event(ev)
+        self.rs_events = []
+        lay = self.layout
+        for n, p in self.params.items():
+            if n.endswith("blocks.0.lambda_param"):
+                continue  # never used by block 0 (model.py:129): the reference leaves .grad = None too
+            if p.grad is None:
+                s, _, ln = lay.shard_range(n, self.rank)
+                p.grad = self.gshard[s:s + ln].view(p.shape)
+
+    # ------------------------------------------------------------------------------ state_dict
+    def full_state_dict(self):
+        """Full, reference-shaped fp32 tensors (all-gathers the master shards when W > 1)."""
+        lay = self.layout
+        out = {}
+        if self.world == 1:
+            full = None
+        for g in range(self.depth + 1):
+            fs, ss = self._group_slices(g)
+            buf = torch.empty(lay.group_numel[g], device=self.device, dtype=torch.float32)
+            self._all_gather(buf, self.master[ss].contiguous())
+            for n, _ in lay.groups[g]:
+                _, off, numel, shape = lay.param[n]
+                out[n] = buf[off:off + numel].view(shape).clone()
+        return out
+
+
+def get_device_mesh():
+    """model.py:475-498 builds a (dp_replicate=1, dp_shard=world) mesh; here it is just the world group."""
+    assert dist.is_initialized()
+    return dist.group.WORLD
+
+
+def apply_fsdp(dit_model, param_dtype, reduce_dtype):
+    """Drop-in for model.py:512-542: shards every parameter group over all ranks (or just flattens them at
+    world size 1, where the reference's own apply_fsdp raises NameError, model.py:489) and returns the model."""
+    flat = FlatShards(dit_model, param_dtype, reduce_dtype)
+    dit_model._flat = flat
+    if flat.world > 1:
+        def _hook(module, state_dict, prefix, local_metadata):
+            if module is dit_model:
+                for n, t in flat.full_state_dict().items():
+                    state_dict[prefix + n] = t
+            return state_dict
+        dit_model._register_state_dict_hook(_hook)
+    return dit_model
