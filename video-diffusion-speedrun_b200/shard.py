@@ -205,6 +205,9 @@ class FlatShards:
                 ev.record(self.comm_stream)
                 self.ag_events[g] = ev
 
+    def mark_dirty(self):
+        self._seen_version = -1
+
     def compute_params(self):
         if self.master._version != self._seen_version:
             self.refresh_from_master()
@@ -288,6 +291,18 @@ def apply_fsdp(dit_model, param_dtype, reduce_dtype):
     world size 1, where the reference's own apply_fsdp raises NameError, model.py:489) and returns the model."""
     flat = FlatShards(dit_model, param_dtype, reduce_dtype)
     dit_model._flat = flat
+    # a stock optimizer (e.g. the reference's optim.AdamW(fused=True), train.py:340-344) writes the fp32 master
+    # views directly: refresh the bf16 compute copy before the next forward.  Our FusedAdamW does it itself.
+    from torch.optim.optimizer import register_optimizer_step_post_hook
+    from .optim import FusedAdamW
+    owned = {id(p) for p in flat.params.values()}
+
+    def _post_step(opt, args, kwargs):
+        if isinstance(opt, FusedAdamW):
+            return
+        if any(id(p) in owned for g in opt.param_groups for p in g["params"]):
+            flat.mark_dirty()
+    dit_model._post_step_hook = register_optimizer_step_post_hook(_post_step)
     if flat.world > 1:
         def _hook(module, state_dict, prefix, local_metadata):
             if module is dit_model:
