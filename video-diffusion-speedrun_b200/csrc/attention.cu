@@ -51,25 +51,32 @@ struct AttnFwdParams {
   float scale_log2;                // head_dim^-0.5 * log2(e)
 };
 
+// Forward v1: one CTA = TWO 128-row query tiles of one (b, head) ("ping-pong"): while the softmax
+// warpgroup of one tile works, the tensor core runs the other tile's GEMMs.
+//   warp 0      TMA producer: Q0,Q1 once; K and V rings (2 stages each, released separately)
+//   warp 1      MMA issuer:   S_t = Q_t K^T (SS), O_t += P_t V (A = P from TMEM, B = V from smem)
+//   warps 4-7   softmax of tile 0, warps 8-11 softmax of tile 1 (thread == query row == TMEM lane)
+// TMEM (512 cols): S0 | S1 | O0 | O1; P_t (bf16, 64 cols) overwrites the head of S_t in place, so P never
+// touches shared memory.  The running max is only refreshed when it grew by more than 2^8 (lazy rescale),
+// which keeps the O correction off the critical path.
+constexpr int FWD_THREADS = 384;
 constexpr int FWD_SMEM = 6 * TILE_BYTES + 256 + 1024;
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw_addr);
-  const uint32_t sQ = base, sK = base + TILE_BYTES, sV = base + 3 * TILE_BYTES, sP = base + 5 * TILE_BYTES;
-  uint8_t* gP = gen + 5 * TILE_BYTES;
+  const uint32_t sQ = base, sK = base + 2 * TILE_BYTES, sV = base + 4 * TILE_BYTES;
   const uint32_t bars = base + 6 * TILE_BYTES;
-  const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, kv_empty = bars + 40,
-                 s_full = bars + 56, s_empty = bars + 72, p_full = bars + 88, pv_done = bars + 96,
-                 tmem_slot = bars + 104;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 6 * TILE_BYTES + 104);
+  const uint32_t q_full = bars, k_full = bars + 8, v_full = bars + 24, k_empty = bars + 40, v_empty = bars + 56,
+                 s_full = bars + 72, p_full = bars + 88, o_done = bars + 104, tmem_slot = bars + 120;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 6 * TILE_BYTES + 120);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
   const int n_kv = (p.Lk + 127) / 128;
 
   if (threadIdx.x == 0) {
@@ -77,12 +84,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full + 8 * s, 1);
       mbar_init(v_full + 8 * s, 1);
-      mbar_init(kv_empty + 8 * s, 1);
+      mbar_init(k_empty + 8 * s, 1);
+      mbar_init(v_empty + 8 * s, 1);
       mbar_init(s_full + 8 * s, 1);
-      mbar_init(s_empty + 8 * s, 128);
+      mbar_init(p_full + 8 * s, 128);
+      mbar_init(o_done + 8 * s, 1);
     }
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
   }
@@ -91,17 +98,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_gen;
-  const uint32_t tS = tmem, tO = tmem + 256;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, TILE_BYTES);
+      mbar_expect_tx(q_full, 2 * TILE_BYTES);
       load_tile_4d(sQ, &tmQ, q_full, q0, head, b);
+      load_tile_4d(sQ + TILE_BYTES, &tmQ, q_full, q0 + 128, head, b);
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
-        mbar_wait(kv_empty + 8 * s, (((j >> 1) & 1) ^ 1));
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(k_empty + 8 * s, ph ^ 1u);
         mbar_expect_tx(k_full + 8 * s, TILE_BYTES);
         load_tile_4d(sK + s * TILE_BYTES, &tmK, k_full + 8 * s, j * 128, head, b);
+        mbar_wait(v_empty + 8 * s, ph ^ 1u);
         mbar_expect_tx(v_full + 8 * s, TILE_BYTES);
         load_tile_4d(sV + s * TILE_BYTES, &tmV, v_full + 8 * s, j * 128, head, b);
       }
@@ -110,107 +119,132 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, false, true);
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(k_full + 8 * s, (j >> 1) & 1);
-        mbar_wait(s_empty + 8 * s, ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
+      auto issue_s = [&](int t, int s) {   // S_t = Q_t K[s]^T
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_bf16(tS + s * 128, desc_kmajor(sQ, kk), desc_kmajor(sK + s * TILE_BYTES, kk), idesc_qk, kk > 0);
-        umma_commit(s_full + 8 * s);
+          umma_bf16(tmem + t * 128, desc_kmajor(sQ + t * TILE_BYTES, kk), desc_kmajor(sK + s * TILE_BYTES, kk),
+                    idesc_qk, kk > 0);
+        umma_commit(s_full + 8 * t);
       };
       mbar_wait(q_full, 0);
-      issue_s(0);
+      mbar_wait(k_full, 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      umma_commit(k_empty);
       for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) issue_s(j + 1);
         const int s = j & 1;
-        mbar_wait(p_full, j & 1);
         mbar_wait(v_full + 8 * s, (j >> 1) & 1);
-        tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16(tO, desc_kmajor(sP, kk), desc_mnmajor(sV + s * TILE_BYTES, kk), idesc_pv, (j > 0 || kk > 0));
-        umma_commit(kv_empty + 8 * s);
-        umma_commit(pv_done);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(p_full + 8 * t, j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)   // O_t += P_t V : A = P (bf16, TMEM, 8 columns per k-step)
+            umma_bf16_ts(tmem + 256 + t * 128, tmem + t * 128 + kk * 8, desc_mnmajor(sV + s * TILE_BYTES, kk),
+                         idesc_pv, (j > 0 || kk > 0));
+          if (t == 1) umma_commit(v_empty + 8 * s);
+          if (j + 1 < n_kv) {
+            if (t == 0) {
+              mbar_wait(k_full + 8 * (s ^ 1), ((j + 1) >> 1) & 1);
+              tc_fence_after();
+            }
+            issue_s(t, s ^ 1);
+            if (t == 1) umma_commit(k_empty + 8 * (s ^ 1));
+          } else {
+            umma_commit(o_done + 8 * t);
+          }
+        }
       }
     }
-  } else {
+  } else if (warp >= 4) {
+    const int t = (warp - 4) >> 2;
     const int quad = warp & 3;
-    const int r = quad * 32 + lane;                 // query row inside the tile == TMEM lane
+    const int r = quad * 32 + lane;                 // row inside the tile == TMEM lane
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem + t * 128 + lane_off, tO = tmem + 256 + t * 128 + lane_off;
+    const float sl2 = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_kv; ++j) {
-      const int s = j & 1;
-      const int valid = p.Lk - j * 128;             // columns >= valid are padding
-      mbar_wait(s_full + 8 * s, (j >> 1) & 1);
+      const int valid = p.Lk - j * 128;             // columns >= valid are padding (last tile only)
+      mbar_wait(s_full + 8 * t, j & 1);
       tc_fence_after();
-      const uint32_t tSj = tS + s * 128 + lane_off;
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
-        tmem_ld32(tSj + c * 32, v);
+        tmem_ld32(tS + c * 32, v);
         tmem_ld_wait();
+        if (valid >= 128) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      uint32_t pk[64];
-      float sum = 0.f;
+      const float mxs = mx * sl2;
+      float alpha = 1.0f;
+      const bool need = mxs > m_run + 8.0f;         // lazy: p stays <= 2^8 otherwise
+      if (need) {
+        alpha = exp2f(m_run - mxs);                 // 0 on the first tile
+        m_run = mxs;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        // S_t(j) complete implies P_t V(j-1) complete (in-order tensor pipe): O_t is stable here
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tO + c * 32, v);
+          tmem_ld_wait();
 #pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st32(tO + c * 32, v);
+        }
+      }
+      l_run *= alpha;
+      float sum = 0.f;
+      const float nm = -m_run;
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
-        tmem_ld32(tSj + c * 32, v);
+        uint32_t pk[16];
+        tmem_ld32(tS + c * 32, v);
         tmem_ld_wait();
+        if (valid >= 128) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c * 32 + i < valid) ? exp2f(__uint_as_float(v[i]) * p.scale_log2 - m_new) : 0.f;
-          float p1 = (c * 32 + i + 1 < valid) ? exp2f(__uint_as_float(v[i + 1]) * p.scale_log2 - m_new) : 0.f;
-          const uint32_t u = pack_bf16x2(p0, p1);
-          const float2 back = unpack_bf16x2(u);     // sum what the tensor core will actually see
-          sum += back.x + back.y;
-          pk[c * 16 + (i >> 1)] = u;
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(s_empty + 8 * s);
-      const float alpha = exp2f(m_run - m_new);     // 0 on the first tile (m_run = -inf)
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);            // P smem free, O holds tiles < j
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tO + lane_off + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st32(tO + lane_off + c * 32, v);
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = exp2f(fmaf(__uint_as_float(v[i]), sl2, nm));
+            const float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), sl2, nm));
+            sum += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
           }
-          tmem_st_wait();
-        }
-      }
+        } else {
 #pragma unroll
-      for (int g = 0; g < 16; ++g)
-        st_tile8(gP, r, g * 8, make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
-      fence_proxy_async_smem();
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c * 32 + i < valid) ? exp2f(fmaf(__uint_as_float(v[i]), sl2, nm)) : 0.f;
+            const float p1 = (c * 32 + i + 1 < valid) ? exp2f(fmaf(__uint_as_float(v[i + 1]), sl2, nm)) : 0.f;
+            sum += p0 + p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+        }
+        tmem_st16(tS + c * 16, pk);                 // P (bf16 pairs) overwrites consumed S columns
+      }
+      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(p_full + 8 * t);
+      l_run += sum;
     }
     // epilogue: O / l -> bf16, token-major
-    mbar_wait(pv_done, (n_kv - 1) & 1);
+    mbar_wait(o_done + 8 * t, 0);
     tc_fence_after();
-    const int row = q0 + r;
+    const int row = q0 + t * 128 + r;
     const float inv_l = 1.0f / l_run;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
-      tmem_ld32(tO + lane_off + c * 32, v);
+      tmem_ld32(tO + c * 32, v);
       tmem_ld_wait();
       if (row < p.Lq) {
         bf16* dst = p.out + ((long long)b * p.Lq + row) * p.ldo + head * HD + c * 32;
@@ -504,8 +538,8 @@ int vds_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   AttnFwdParams p;
   p.out = (bf16*)out; p.ldo = ldo; p.lse = lse; p.Lq = Lq; p.Lk = Lk; p.nh = nh;
   p.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid((Lq + 127) / 128, nh, B);
-  attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  dim3 grid((Lq + 255) / 256, nh, B);
+  attn_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
   VDS_CHECK_LAUNCH("attn_fwd");
   return VDS_OK;
 }
