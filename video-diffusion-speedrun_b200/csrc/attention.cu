@@ -290,7 +290,6 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __r
 
 struct AttnBwdParams {
   const float* lse; const float* delta;   // [B, nh, Lq]
-  float* dq_acc; long long lddq;           // fp32 [B, Lq, lddq] (+= via red)
   bf16* dk; long long lddk;                // bf16 [B, Lk, lddk], head at head*128 (q_splits == 1)
   bf16* dv; long long lddv;
   float* dk_acc; float* dv_acc; long long ldkv_acc;  // fp32 accumulation targets when q_splits > 1
@@ -298,53 +297,75 @@ struct AttnBwdParams {
   float scale_log2, scale;
 };
 
-constexpr int BWD_SMEM = 6 * TILE_BYTES + 1024 /*lse+delta*/ + 256 + 1024;
+// Backward v1.  CTA = one 128-row K/V tile of one (b, head), looping over 64-row query sub-tiles:
+//   S^T = K Q^T, dP^T = V dO^T          (TMEM, double-buffered)        M=128 (kv) N=64 (q)  K=128 (d)
+//   P^T, dS^T -> bf16 smem (SW128)      (compute warpgroup, thread == kv row)
+//   dV += P^T dO, dK += dS^T Q          (TMEM accumulators)            M=128 (kv) N=128 (d) K=64 (q)
+//   dQ^T = K^T dS^T                     (TMEM, aliases the S^T buffer) M=128 (d)  N=64 (q)  K=128 (kv)
+//   dQ^T -> fp32 smem tile [q][d] -> cp.reduce.async.bulk.tensor (TMA adds it into the fp32 dq buffer)
+// warp 0 TMA producer (K,V once; Q/dO ring of 3) | warp 1 MMA issuer | warps 4-7 compute | warps 8-11 dQ drain.
+constexpr int BWD_THREADS = 384;
+constexpr int QSUB = 64;
+constexpr int QT_BYTES = QSUB * HD * 2;          // 16 KiB: 64 x 128 bf16 (two [64 x 128 B] halves)
+constexpr int QT_HALF = QT_BYTES / 2;            // 8 KiB
+constexpr int PT_BYTES = 128 * QSUB * 2;         // 16 KiB: [128 kv rows x 128 B]
+constexpr int STG_BYTES = QSUB * HD * 4;         // 32 KiB fp32 staging of one dQ sub-tile
+constexpr int BWD_OFF_Q = 2 * TILE_BYTES;                    // 3 stages x (Q, dO)
+constexpr int BWD_OFF_PT = BWD_OFF_Q + 3 * 2 * QT_BYTES;
+constexpr int BWD_OFF_DST = BWD_OFF_PT + PT_BYTES;
+constexpr int BWD_OFF_STG = BWD_OFF_DST + PT_BYTES;
+constexpr int BWD_OFF_STAT = BWD_OFF_STG + STG_BYTES;       // [2][2][64] floats
+constexpr int BWD_OFF_BAR = BWD_OFF_STAT + 1024;
+constexpr int BWD_SMEM = BWD_OFF_BAR + 256 + 1024;
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmDQ, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw_addr);
-  const uint32_t sK = base, sV = base + TILE_BYTES, sQ = base + 2 * TILE_BYTES, sDO = base + 3 * TILE_BYTES,
-                 sPT = base + 4 * TILE_BYTES, sDST = base + 5 * TILE_BYTES;
-  uint8_t* gPT = gen + 4 * TILE_BYTES;
-  uint8_t* gDST = gen + 5 * TILE_BYTES;
-  float* s_lse = reinterpret_cast<float*>(gen + 6 * TILE_BYTES);
-  float* s_delta = s_lse + 128;
-  const uint32_t bars = base + 6 * TILE_BYTES + 1024;
-  const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 16, sdp_full = bars + 24,
-                 pds_full = bars + 32, dq_full = bars + 40, dq_drained = bars + 48, tmem_slot = bars + 56;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + 6 * TILE_BYTES + 1024 + 56);
+  const uint32_t sK = base, sV = base + TILE_BYTES, sQ = base + BWD_OFF_Q, sPT = base + BWD_OFF_PT,
+                 sDST = base + BWD_OFF_DST, sSTG = base + BWD_OFF_STG;
+  uint8_t* gPT = gen + BWD_OFF_PT;
+  uint8_t* gDST = gen + BWD_OFF_DST;
+  float* gSTG = reinterpret_cast<float*>(gen + BWD_OFF_STG);
+  float* s_stat = reinterpret_cast<float*>(gen + BWD_OFF_STAT);   // [buf][lse|delta][64]
+  const uint32_t bars = base + BWD_OFF_BAR;
+  const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 32, sdp_full = bars + 56,
+                 pds_full = bars + 72, mma_done = bars + 80, dq_drained = bars + 96, tmem_slot = bars + 112;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + BWD_OFF_BAR + 112);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv_tile = blockIdx.x / p.q_splits, split = blockIdx.x % p.q_splits;
   const int head = blockIdx.y, b = blockIdx.z;
   const int kv0 = kv_tile * 128;
-  const int n_q_all = (p.Lq + 127) / 128;
+  const int n_q_all = (p.Lq + QSUB - 1) / QSUB;
   const int per = (n_q_all + p.q_splits - 1) / p.q_splits;
   const int qt0 = split * per, qt1 = min(n_q_all, qt0 + per);
   const int n_q = qt1 - qt0;
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
-    mbar_init(qdo_full, 1);
-    mbar_init(qdo_empty, 1);
-    mbar_init(sdp_full, 1);
+    for (int s = 0; s < 3; ++s) { mbar_init(qdo_full + 8 * s, 1); mbar_init(qdo_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(sdp_full + 8 * s, 1);
+      mbar_init(mma_done + 8 * s, 1);
+      mbar_init(dq_drained + 8 * s, 128);
+    }
     mbar_init(pds_full, 128);
-    mbar_init(dq_full, 1);
-    mbar_init(dq_drained, 128);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_gen;
-  const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 384, tDQ = tmem;
+  const uint32_t tDV = tmem, tDK = tmem + 128;
+  // buffer bb: S^T at 256 + bb*128 (64 cols, later reused for dQ^T), dP^T right behind it (64 cols)
 
   if (n_q > 0) {
     if (warp == 0) {
@@ -353,148 +374,196 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         load_tile_4d(sK, &tmK, kv_full, kv0, head, b);
         load_tile_4d(sV, &tmV, kv_full, kv0, head, b);
         for (int i = 0; i < n_q; ++i) {
-          mbar_wait(qdo_empty, (i & 1) ^ 1);
-          mbar_expect_tx(qdo_full, 2 * TILE_BYTES);
-          load_tile_4d(sQ, &tmQ, qdo_full, (qt0 + i) * 128, head, b);
-          load_tile_4d(sDO, &tmDO, qdo_full, (qt0 + i) * 128, head, b);
+          const int st = i % 3;
+          const uint32_t us = (i / 3) & 1;
+          mbar_wait(qdo_empty + 8 * st, us ^ 1u);
+          mbar_expect_tx(qdo_full + 8 * st, 2 * QT_BYTES);
+          const uint32_t dq = sQ + st * 2 * QT_BYTES, dd = dq + QT_BYTES;
+          const int row0 = (qt0 + i) * QSUB;
+          tma_load_4d(dq, &tmQ, qdo_full + 8 * st, 0, row0, head, b);
+          tma_load_4d(dq + QT_HALF, &tmQ, qdo_full + 8 * st, 64, row0, head, b);
+          tma_load_4d(dd, &tmDO, qdo_full + 8 * st, 0, row0, head, b);
+          tma_load_4d(dd + QT_HALF, &tmDO, qdo_full + 8 * st, 64, row0, head, b);
         }
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, false, false);
-        constexpr uint32_t idesc_kmn = umma_idesc_bf16(128, 128, false, true);
-        constexpr uint32_t idesc_mnmn = umma_idesc_bf16(128, 128, true, true);
-        mbar_wait(kv_full, 0);
-        for (int i = 0; i < n_q; ++i) {
-          mbar_wait(qdo_full, i & 1);
-          if (i > 0) mbar_wait(dq_drained, (i - 1) & 1);   // dQ(i-1) left the S^T columns
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);     // S^T, dP^T
+        constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, false, true);   // dV, dK
+        constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, true, true);      // dQ^T
+        auto issue_sdp = [&](int k) {
+          const int bb = k & 1, st = k % 3;
+          mbar_wait(qdo_full + 8 * st, (k / 3) & 1);
+          if (k >= 2) mbar_wait(dq_drained + 8 * bb, ((k >> 1) - 1) & 1);
           tc_fence_after();
+          const uint32_t q = sQ + st * 2 * QT_BYTES, d_o = q + QT_BYTES;
+          const uint32_t tST = tmem + 256 + bb * 128, tDPT = tST + 64;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // S^T = K Q^T
-            umma_bf16(tST, desc_kmajor(sK, kk), desc_kmajor(sQ, kk), idesc_kk, kk > 0);
+          for (int kk = 0; kk < 8; ++kk)   // S^T = K Q^T : B = Q tile, K-major, 64 rows per half
+            umma_bf16(tST, desc_kmajor(sK, kk), umma_smem_desc(q + (kk >> 2) * QT_HALF + (kk & 3) * 32, 16, 1024),
+                      idesc_s, kk > 0);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)   // dP^T = V dO^T
-            umma_bf16(tDPT, desc_kmajor(sV, kk), desc_kmajor(sDO, kk), idesc_kk, kk > 0);
-          umma_commit(sdp_full);
+            umma_bf16(tDPT, desc_kmajor(sV, kk), umma_smem_desc(d_o + (kk >> 2) * QT_HALF + (kk & 3) * 32, 16, 1024),
+                      idesc_s, kk > 0);
+          umma_commit(sdp_full + 8 * bb);
+        };
+        mbar_wait(kv_full, 0);
+        issue_sdp(0);
+        for (int i = 0; i < n_q; ++i) {
+          const int bb = i & 1, st = i % 3;
+          if (i + 1 < n_q) issue_sdp(i + 1);
           mbar_wait(pds_full, i & 1);
           tc_fence_after();
+          const uint32_t q = sQ + st * 2 * QT_BYTES, d_o = q + QT_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dV += P^T dO
-            umma_bf16(tDV, desc_kmajor(sPT, kk), desc_mnmajor(sDO, kk), idesc_kmn, (i > 0 || kk > 0));
+          for (int kk = 0; kk < 4; ++kk)   // dV += P^T dO : A = P^T [128 x 64] K-major, B = dO MN-major (N = d)
+            umma_bf16(tDV, umma_smem_desc(sPT + kk * 32, 16, 1024), umma_smem_desc(d_o + kk * 2048, QT_HALF, 1024),
+                      idesc_acc, (i > 0 || kk > 0));
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dK += dS^T Q
-            umma_bf16(tDK, desc_kmajor(sDST, kk), desc_mnmajor(sQ, kk), idesc_kmn, (i > 0 || kk > 0));
+          for (int kk = 0; kk < 4; ++kk)   // dK += dS^T Q
+            umma_bf16(tDK, umma_smem_desc(sDST + kk * 32, 16, 1024), umma_smem_desc(q + kk * 2048, QT_HALF, 1024),
+                      idesc_acc, (i > 0 || kk > 0));
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dQ = dS K  (A = dS^T read MN-major, B = K read MN-major)
-            umma_bf16(tDQ, desc_mnmajor(sDST, kk), desc_mnmajor(sK, kk), idesc_mnmn, kk > 0);
-          umma_commit(qdo_empty);          // every operand tile of this iteration has been consumed
-          umma_commit(dq_full);
+          for (int kk = 0; kk < 8; ++kk)   // dQ^T = K^T dS^T : A = K MN-major (M = d), B = dS^T MN-major (N = q)
+            umma_bf16(tmem + 256 + bb * 128, desc_mnmajor(sK, kk), umma_smem_desc(sDST + kk * 2048, 16, 1024),
+                      idesc_dq, kk > 0);
+          umma_commit(qdo_empty + 8 * st);
+          umma_commit(mma_done + 8 * bb);
         }
       }
-    } else {
+    } else if (warp >= 4 && warp < 8) {
+      // ------------------------------------------------------------ compute warpgroup (thread == kv row)
       const int quad = warp & 3;
       const int r = quad * 32 + lane;
-      const int ct = threadIdx.x - 64;     // 0..127
+      const int ct = threadIdx.x - 128;    // 0..127
       const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
       const bool kv_ok = (kv0 + r) < p.Lk;
       const long long stat_base = ((long long)b * p.nh + head) * p.Lq;
+      const float* stat_src = (ct < 64 ? p.lse : p.delta) + stat_base;
+      const int sc = ct & 63;
+      {
+        const int q = qt0 * QSUB + sc;
+        s_stat[(ct < 64 ? 0 : 64) + sc] = q < p.Lq ? stat_src[q] : 0.f;
+      }
       for (int i = 0; i < n_q; ++i) {
-        const int q0 = (qt0 + i) * 128;
-        // stage lse / delta of this query tile (previous iteration's readers are past the named barrier below)
-        {
-          const int q = q0 + ct;
-          s_lse[ct] = q < p.Lq ? p.lse[stat_base + q] : 0.f;
-          s_delta[ct] = q < p.Lq ? p.delta[stat_base + q] : 0.f;
+        const int bb = i & 1;
+        const int q0 = (qt0 + i) * QSUB;
+        float next_stat = 0.f;
+        if (i + 1 < n_q) {
+          const int q = q0 + QSUB + sc;
+          next_stat = q < p.Lq ? stat_src[q] : 0.f;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        mbar_wait(sdp_full, i & 1);
+        named_bar_sync(1, 128);            // stats of this sub-tile visible; previous iteration fully done
+        const float* lse_s = s_stat + bb * 128;
+        const float* del_s = lse_s + 64;
+        mbar_wait(sdp_full + 8 * bb, (i >> 1) & 1);
         tc_fence_after();
         const int qvalid = p.Lq - q0;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        const uint32_t tST = tmem + 256 + bb * 128 + lane_off, tDPT = tST + 64;
+        uint32_t pp[32], dd[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
           uint32_t sv[32], dv[32];
-          tmem_ld32(tST + lane_off + c * 32, sv);
-          tmem_ld32(tDPT + lane_off + c * 32, dv);
+          tmem_ld32(tST + c * 32, sv);
+          tmem_ld32(tDPT + c * 32, dv);
           tmem_ld_wait();
-          uint32_t pp[16], dd[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             float pv[2], ds[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int col = c * 32 + e + u;
-              const bool ok = kv_ok && (col < qvalid);
-              const float pr = ok ? exp2f(__uint_as_float(sv[e + u]) * p.scale_log2 - s_lse[col]) : 0.f;
+              float pr = exp2f(fmaf(__uint_as_float(sv[e + u]), p.scale_log2, -lse_s[col]));
+              pr = (kv_ok && col < qvalid) ? pr : 0.f;
               pv[u] = pr;
-              ds[u] = pr * (__uint_as_float(dv[e + u]) - s_delta[col]) * p.scale;
+              ds[u] = pr * (__uint_as_float(dv[e + u]) - del_s[col]) * p.scale;
             }
-            pp[e >> 1] = pack_bf16x2(pv[0], pv[1]);
-            dd[e >> 1] = pack_bf16x2(ds[0], ds[1]);
+            pp[c * 16 + (e >> 1)] = pack_bf16x2(pv[0], pv[1]);
+            dd[c * 16 + (e >> 1)] = pack_bf16x2(ds[0], ds[1]);
           }
+        }
+        if (i > 0) mbar_wait(mma_done + 8 * (bb ^ 1), ((i - 1) >> 1) & 1);   // P^T / dS^T smem consumed
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            st_tile8(gPT, r, c * 32 + g * 8, make_uint4(pp[g * 4], pp[g * 4 + 1], pp[g * 4 + 2], pp[g * 4 + 3]));
-            st_tile8(gDST, r, c * 32 + g * 8, make_uint4(dd[g * 4], dd[g * 4 + 1], dd[g * 4 + 2], dd[g * 4 + 3]));
-          }
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t off = sw128_offset(r, g);
+          *reinterpret_cast<uint4*>(gPT + off) = make_uint4(pp[g * 4], pp[g * 4 + 1], pp[g * 4 + 2], pp[g * 4 + 3]);
+          *reinterpret_cast<uint4*>(gDST + off) = make_uint4(dd[g * 4], dd[g * 4 + 1], dd[g * 4 + 2], dd[g * 4 + 3]);
         }
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(pds_full);
-        // drain dQ tile: TMEM lane == query row
-        mbar_wait(dq_full, i & 1);
+        if (i + 1 < n_q) s_stat[(bb ^ 1) * 128 + (ct < 64 ? 0 : 64) + sc] = next_stat;
+      }
+    } else if (warp >= 8) {
+      // ------------------------------------------------------------ dQ drain warpgroup (thread == d)
+      const int quad = warp & 3;
+      const int d = quad * 32 + lane;
+      const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+      const bool leader = threadIdx.x == 256;
+      for (int i = 0; i < n_q; ++i) {
+        const int bb = i & 1;
+        mbar_wait(mma_done + 8 * bb, (i >> 1) & 1);
         tc_fence_after();
-        const int qrow = q0 + r;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tmem + 256 + bb * 128 + lane_off, v0);
+        tmem_ld32(tmem + 256 + bb * 128 + lane_off + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dq_drained + 8 * bb);
+        if (leader) bulk_wait_group_read0();      // previous reduction has finished reading the staging tile
+        named_bar_sync(2, 128);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          gSTG[q * HD + d] = __uint_as_float(v0[q]);
+          gSTG[(q + 32) * HD + d] = __uint_as_float(v1[q]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (leader) {
+          tma_reduce_add_4d(&tmDQ, sSTG, 0, (qt0 + i) * QSUB, head, b);
+          bulk_commit_group();
+        }
+      }
+      if (leader) bulk_wait_group0();
+    }
+    if (warp >= 4) {
+      // dK (compute warpgroup) / dV (drain warpgroup): TMEM lane == kv row
+      const int which = warp >= 8 ? 1 : 0;
+      const int quad = warp & 3;
+      const int r = quad * 32 + lane;
+      const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+      mbar_wait(mma_done + 8 * ((n_q - 1) & 1), ((n_q - 1) >> 1) & 1);
+      tc_fence_after();
+      const int krow = kv0 + r;
+      const uint32_t t = (which == 0 ? tDK : tDV) + lane_off;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tDQ + lane_off + c * 32, v);
-          tmem_ld_wait();
-          if (qrow < p.Lq) {
-            float* dst = p.dq_acc + ((long long)b * p.Lq + qrow) * p.lddq + head * HD + c * 32;
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t + c * 32, v);
+        tmem_ld_wait();
+        if (krow < p.Lk) {
+          if (p.q_splits == 1) {
+            bf16* dst = (which == 0 ? p.dk + ((long long)b * p.Lk + krow) * p.lddk
+                                    : p.dv + ((long long)b * p.Lk + krow) * p.lddv) + head * HD + c * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+              u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+              u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+              u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+              *reinterpret_cast<uint4*>(dst + g * 8) = u;
+            }
+          } else {
+            float* dst = (which == 0 ? p.dk_acc : p.dv_acc) + ((long long)b * p.Lk + krow) * p.ldkv_acc +
+                         head * HD + c * 32;
 #pragma unroll
             for (int g = 0; g < 8; ++g)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
                            "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
                            "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
                            : "memory");
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(dq_drained);
-      }
-      // dK / dV of this K/V tile (all MMAs complete: dq_full of the last iteration was waited above)
-      const int krow = kv0 + r;
-#pragma unroll 1
-      for (int which = 0; which < 2; ++which) {
-        const uint32_t t = (which == 0 ? tDK : tDV) + lane_off;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t + c * 32, v);
-          tmem_ld_wait();
-          if (krow < p.Lk) {
-            if (p.q_splits == 1) {
-              bf16* dst = (which == 0 ? p.dk + ((long long)b * p.Lk + krow) * p.lddk
-                                      : p.dv + ((long long)b * p.Lk + krow) * p.lddv) + head * HD + c * 32;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint4 u;
-                u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
-                u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
-                u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
-                u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
-                *reinterpret_cast<uint4*>(dst + g * 8) = u;
-              }
-            } else {
-              float* dst = (which == 0 ? p.dk_acc : p.dv_acc) + ((long long)b * p.Lk + krow) * p.ldkv_acc +
-                           head * HD + c * 32;
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
-                             "f"(__uint_as_float(v[g * 4])), "f"(__uint_as_float(v[g * 4 + 1])),
-                             "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
-                             : "memory");
-            }
           }
         }
       }
@@ -505,11 +574,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-static int make_tmap_tokens(CUtensorMap* tm, const void* ptr, long long ld, int L, int nh, int B) {
+static int make_tmap_tokens(CUtensorMap* tm, const void* ptr, long long ld, int L, int nh, int B, int box_rows = 128) {
   uint64_t dims[4] = {(uint64_t)HD, (uint64_t)L, (uint64_t)nh, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)HD * 2, (uint64_t)L * (uint64_t)ld * 2};
-  uint32_t box[4] = {64, 128, 1, 1};
+  uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
   return encode_tmap_bf16(tm, ptr, 4, dims, strides, box);
+}
+// fp32 [B, L, ld] accumulation buffer, box = one [64 rows x 128 floats] sub-tile of one head, no swizzle
+static int make_tmap_dq(CUtensorMap* tm, const float* ptr, long long ld, int L, int nh, int B) {
+  uint64_t dims[4] = {(uint64_t)HD, (uint64_t)L, (uint64_t)nh, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)ld * 4, (uint64_t)HD * 4, (uint64_t)L * (uint64_t)ld * 4};
+  uint32_t box[4] = {(uint32_t)HD, (uint32_t)QSUB, 1, 1};
+  return encode_tmap(tm, ptr, 1, 4, dims, strides, box, 0);
 }
 
 }  // namespace vds
@@ -554,12 +630,14 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   VDS_CHECK_ARG(head_dim == HD, "attn_bwd: head_dim=%d unsupported (only 128)", head_dim);
   VDS_CHECK_ARG(q_splits >= 1, "attn_bwd: q_splits");
   VDS_CHECK_ARG(q_splits == 1 ? (dk && dv) : (dk_acc && dv_acc), "attn_bwd: missing dk/dv target");
-  CUtensorMap tq, tk, tv, tdo;
+  VDS_CHECK_ARG(lddq % 4 == 0 && ((uintptr_t)dq_acc & 15) == 0, "attn_bwd: dq_acc must be 16-byte aligned, lddq %% 4 == 0");
+  CUtensorMap tq, tk, tv, tdo, tdq;
   int r;
-  if ((r = make_tmap_tokens(&tq, q, ldq, Lq, nh, B))) return r;
+  if ((r = make_tmap_tokens(&tq, q, ldq, Lq, nh, B, QSUB))) return r;
   if ((r = make_tmap_tokens(&tk, k, ldk, Lk, nh, B))) return r;
   if ((r = make_tmap_tokens(&tv, v, ldv, Lk, nh, B))) return r;
-  if ((r = make_tmap_tokens(&tdo, d_o, lddo, Lq, nh, B))) return r;
+  if ((r = make_tmap_tokens(&tdo, d_o, lddo, Lq, nh, B, QSUB))) return r;
+  if ((r = make_tmap_dq(&tdq, dq_acc, lddq, Lq, nh, B))) return r;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
@@ -573,13 +651,13 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
     VDS_CHECK_LAUNCH("attn_bwd_prep");
   }
   AttnBwdParams p;
-  p.lse = lse; p.delta = delta; p.dq_acc = dq_acc; p.lddq = lddq;
+  p.lse = lse; p.delta = delta;
   p.dk = (bf16*)dk; p.lddk = lddk; p.dv = (bf16*)dv; p.lddv = lddv;
   p.dk_acc = dk_acc; p.dv_acc = dv_acc; p.ldkv_acc = ldkv_acc;
   p.Lq = Lq; p.Lk = Lk; p.nh = nh; p.q_splits = q_splits;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(((Lk + 127) / 128) * q_splits, nh, B);
-  attn_bwd_kernel<<<grid, ATT_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, tdo, p);
+  attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, tdo, tdq, p);
   VDS_CHECK_LAUNCH("attn_bwd");
   return VDS_OK;
 }

@@ -50,6 +50,11 @@ static encode_fn_t get_encode_fn() {
 
 int encode_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tmap(tm, base, 0, rank, dims, strides_bytes, box, 1);
+}
+
+int encode_tmap(CUtensorMap* tm, const void* base, int is_f32, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
   encode_fn_t fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled not available (no CUDA driver / no GPU): there is no CPU fallback");
@@ -65,8 +70,9 @@ int encode_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t
     es[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = fn(tm, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+                  const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu box %u,%u stride0 %llu)",

@@ -18,6 +18,10 @@ int num_sms();
 int encode_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box);
 
+// general form: fp32 or bf16 elements, 128-B swizzle or none
+int encode_tmap(CUtensorMap* tm, const void* base, int is_f32, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
+
 #define VDS_CHECK_ARG(cond, ...)        \
   do {                                  \
     if (!(cond)) {                      \
