@@ -292,7 +292,11 @@ def main():
     ap.add_argument("--workload", default="debug-8k", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", type=int, default=0, help="profiling only: override the model depth (NOT a bench line)")
     args = ap.parse_args()
+    if args.depth > 0:
+        hidden, depth, heads, B, thw = WORKLOADS[args.workload]
+        WORKLOADS[args.workload] = (hidden, args.depth, heads, B, thw)
     if args.impl == "reference":
         run_reference(args)
     else:

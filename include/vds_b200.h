@@ -73,6 +73,7 @@ typedef struct vds_gemm_args {
    * r % remap_rows; remap_rows == 0 -> identity.  Used to write patch tokens behind the register
    * tokens (model.py:362) without a concat copy. */
   int32_t remap_rows, remap_stride, remap_offset;
+  int32_t tile_n; /* 0 = automatic (128 or 256), 128 = force 128-wide tiles (tuning / tests) */
 } vds_gemm_args;
 
 int vds_gemm(const vds_gemm_args* args, void* stream);

@@ -100,3 +100,26 @@ def test_gemm_remap_rows(cuda_dev):
     ref = (a.float() @ w.float().t() + bias.float()).view(Bt, Np, h)
     _close(out[:, 16:], ref)
     assert out[:, :16].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("tile_n", [0, 128])
+def test_gemm_wide_tiles_epilogues(cuda_dev, tile_n):
+    """128 x 256 tiles (auto) vs forced 128 x 128 on shapes large enough to pick the wide path."""
+    from vds_b200 import ops, lib
+    M, h = 4 * 4104, 512
+    a, w1, b1 = _mk((M, h), cuda_dev, 30), _mk((4 * h, h), cuda_dev, 31, 0.05), _mk((4 * h,), cuda_dev, 32)
+    pre, act = ops.gemm(a, w1, bias=b1, epilogue=lib.EPI_BIAS_GELU, tile_n=tile_n)
+    ref_pre = (a.float() @ w1.float().t() + b1.float()).bfloat16()
+    _close(pre, ref_pre)
+    _close(act, torch.nn.functional.gelu(pre.float()), tol=1e-2)
+    w2, x, gate = _mk((h, 4 * h), cuda_dev, 33, 0.05), _mk((M, h), cuda_dev, 34), _mk((4, 9 * h), cuda_dev, 35)
+    g = gate[:, 8 * h:]
+    lin, xo = ops.gemm(act, w2, epilogue=lib.EPI_GATE_RES, aux=x, gate=g, rows_per_batch=4104, tile_n=tile_n)
+    ref_lin = (act.float() @ w2.float().t()).bfloat16()
+    _close(lin, ref_lin)
+    _close(xo, x + (lin.view(4, 4104, h) * g[:, None, :]).view(M, h), tol=1e-2)
+    dy = _mk((M, h), cuda_dev, 36)
+    dh = ops.gemm(dy, w2, b_mn=True, epilogue=lib.EPI_DGELU, aux=pre, tile_n=tile_n)
+    hh = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(hh).backward(dy.float() @ w2.float())
+    _close(dh, hh.grad)

@@ -340,19 +340,28 @@ static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
   return VDS_OK;
 }
 
+// 128 x 256 tiles double the flops per operand byte (the K = 512 GEMMs of the debug model are L2-bandwidth
+// bound with 128 x 128 tiles); used when N is a multiple of 256 and there are enough tiles to fill the chip.
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_bn(const vds_gemm_args& a, cudaStream_t s) {
+  const long long tiles256 = (long long)((a.M + BM - 1) / BM) * (a.N / 256);
+  if (a.N % 256 == 0 && tiles256 >= num_sms() && a.tile_n != 128) return launch_gemm<256, A_MN, B_MN, EPI>(a, s);
+  return launch_gemm<128, A_MN, B_MN, EPI>(a, s);
+}
+
 template <bool A_MN, bool B_MN>
 static int dispatch_epi(const vds_gemm_args& a, cudaStream_t s) {
   switch (a.epilogue) {
-    case VDS_EPI_STORE: return launch_gemm<128, A_MN, B_MN, VDS_EPI_STORE>(a, s);
+    case VDS_EPI_STORE: return launch_bn<A_MN, B_MN, VDS_EPI_STORE>(a, s);
     case VDS_EPI_ACCUM_F32: return launch_gemm<128, A_MN, B_MN, VDS_EPI_ACCUM_F32>(a, s);
     case VDS_EPI_STORE_F32: return launch_gemm<128, A_MN, B_MN, VDS_EPI_STORE_F32>(a, s);
     default: break;
   }
   if constexpr (!A_MN) {
     switch (a.epilogue) {
-      case VDS_EPI_BIAS_GELU: if constexpr (!B_MN) return launch_gemm<128, A_MN, B_MN, VDS_EPI_BIAS_GELU>(a, s); break;
-      case VDS_EPI_GATE_RES: if constexpr (!B_MN) return launch_gemm<128, A_MN, B_MN, VDS_EPI_GATE_RES>(a, s); break;
-      case VDS_EPI_DGELU: if constexpr (B_MN) return launch_gemm<128, A_MN, B_MN, VDS_EPI_DGELU>(a, s); break;
+      case VDS_EPI_BIAS_GELU: if constexpr (!B_MN) return launch_bn<A_MN, B_MN, VDS_EPI_BIAS_GELU>(a, s); break;
+      case VDS_EPI_GATE_RES: if constexpr (!B_MN) return launch_bn<A_MN, B_MN, VDS_EPI_GATE_RES>(a, s); break;
+      case VDS_EPI_DGELU: if constexpr (B_MN) return launch_bn<A_MN, B_MN, VDS_EPI_DGELU>(a, s); break;
       default: break;
     }
   }
