@@ -505,22 +505,44 @@ __global__ void qkv_post_bwd_kernel(const QkvPostBwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------------- column sums
-// out[n] += sum_rows x[row, n]  (bias gradients), x bf16 [rows, ld], out fp32
+// out[n] += sum_rows x[row, n]  (bias gradients), x bf16 [rows, ld], out fp32.
+// CTA = 256 columns x `rows_per_cta` rows: a warp reads one 512-byte row segment per step (4 rows in flight),
+// the 8 warps meet in shared memory, one atomicAdd per column per CTA.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long rows,
                                                      int n, long long ld, int rows_per_cta) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (c >= n) return;
+  __shared__ float red[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 256 + lane * 8;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
   const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long r = r0; r < r1; ++r) {
-    float v[8];
-    ld8(x + r * ld + c, v);
+  if (c < n) {
+    long long r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      float v0[8], v1[8], v2[8], v3[8];
+      ld8(x + r * ld + c, v0);
+      ld8(x + (r + 8) * ld + c, v1);
+      ld8(x + (r + 16) * ld + c, v2);
+      ld8(x + (r + 24) * ld + c, v3);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      for (int j = 0; j < 8; ++j) acc[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+    }
+    for (; r < r1; r += 8) {
+      float v[8];
+      ld8(x + r * ld + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(&out[c + j], acc[j]);
+  for (int j = 0; j < 8; ++j) red[warp][lane + 32 * j] = acc[j];   // conflict-free: [j][lane] order
+  __syncthreads();
+  const int t = threadIdx.x;          // t = lane' + 32*j'  -> column lane'*8 + j'
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][t];
+  const int col = blockIdx.x * 256 + (t & 31) * 8 + (t >> 5);
+  if (col < n) atomicAdd(&out[col], s);
 }
 
 // out[r, :] (+)= sum_b x[b, r, :]   (register-token gradient: rows 0..15 of every sample)
@@ -705,9 +727,9 @@ int vds_qkv_post_bwd(void* dqkv, const float* dq_acc, const float* cos, const fl
 
 int vds_colsum(const void* x, float* out, int64_t rows, int n, int64_t ld, void* stream) {
   VDS_CHECK_ARG(n % 8 == 0 && ld % 8 == 0, "colsum: n, ld must be multiples of 8");
-  const int col_ctas = ceil_div(n / 8, 256);
-  int row_chunks = max(1, (4 * num_sms()) / col_ctas);
-  int rows_per_cta = max(32, ceil_div(rows, row_chunks));
+  const int col_ctas = ceil_div(n, 256);
+  int row_chunks = max(1, (2 * num_sms()) / col_ctas);
+  int rows_per_cta = max(64, ceil_div(rows, row_chunks));
   dim3 grid(col_ctas, ceil_div(rows, rows_per_cta));
   colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, out, rows, n, ld, rows_per_cta);
   VDS_CHECK_LAUNCH("colsum");

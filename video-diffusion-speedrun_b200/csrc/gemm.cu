@@ -20,7 +20,7 @@ namespace vds {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quadrant)
 
 template <int BN>
 struct GemmCfg {
@@ -29,7 +29,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int STG_BYTES = 8 * 4096;  // per epilogue warp: 32 rows x 128 B transpose buffer
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -49,13 +50,28 @@ struct GemmDev {
   int remap_rows, remap_stride, remap_offset;
 };
 
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 rounding of the outputs): the libm
+// erff costs ~4x more instructions and made the GELU epilogues, not the MMAs, the bottleneck of the MLP GEMMs.
+// Returns erf(x/sqrt2) and exp(-x^2/2) (shared by GELU and its derivative).
+__device__ __forceinline__ float erf_as(float x, float& gauss) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  gauss = exp2f(-0.72134752044448170368f * x * x);   // exp(-x^2/2) = exp(-z^2)
+  const float e = fmaf(-poly * t, gauss, 1.0f);
+  return copysignf(e, x);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  float g;
+  return 0.5f * x * (1.0f + erf_as(x, g));
 }
 __device__ __forceinline__ float dgelu_erf(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float g;
+  const float cdf = 0.5f * (1.0f + erf_as(x, g));
+  return fmaf(x * 0.39894228040143267794f, g, cdf);
 }
 
 __device__ __forceinline__ void ld8_bf16(const bf16* p, float (&o)[8]) {
@@ -74,6 +90,131 @@ __device__ __forceinline__ void st8_bf16(bf16* p, const float (&v)[8]) {
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
+}
+
+// ---- coalesced bf16 epilogue -------------------------------------------------------------------------------
+// TMEM hands each thread one output ROW; storing rows straight from registers makes every warp store touch 32
+// different lines (32 partial-sector transactions), which caps the K = 512 GEMMs well below the MMA rate.  Each
+// epilogue warp therefore transposes 32 rows x 64 columns through a private 4 KiB shared-memory buffer
+// (16-byte chunks XOR-swizzled by row) so that one warp instruction moves 4 full 128-byte row segments.
+__device__ __forceinline__ uint32_t stg_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+struct RowMap {   // global row of local row rr (0..31) for loads / stores, -1 if out of range
+  int row0, M, remap_rows, remap_stride, remap_offset;
+  __device__ __forceinline__ long long out_row(int rr) const {
+    const int r = row0 + rr;
+    if (r >= M) return -1;
+    if (remap_rows > 0) return (long long)(r / remap_rows) * remap_stride + remap_offset + r % remap_rows;
+    return r;
+  }
+  __device__ __forceinline__ long long in_row(int rr) const { return row0 + rr < M ? row0 + rr : -1; }
+};
+
+// staging -> global: 8 instructions, lane = (row within group of 4, 16-byte chunk)
+__device__ __forceinline__ void stg_store(const uint8_t* stg, bf16* C, long long ldc, const RowMap& rm, int col0,
+                                          int N, int lane, bool remap) {
+  const int ch = lane & 7, col = col0 + ch * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int rr = k * 4 + (lane >> 3);
+    const long long row = remap ? rm.out_row(rr) : rm.in_row(rr);
+    const uint4 v = *reinterpret_cast<const uint4*>(stg + stg_off(rr, ch));
+    if (row >= 0 && col < N) *reinterpret_cast<uint4*>(C + row * ldc + col) = v;
+  }
+}
+// global -> staging
+__device__ __forceinline__ void stg_load(uint8_t* stg, const bf16* A, long long lda, const RowMap& rm, int col0, int N,
+                                         int lane) {
+  const int ch = lane & 7, col = col0 + ch * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int rr = k * 4 + (lane >> 3);
+    const long long row = rm.in_row(rr);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row >= 0 && col < N) v = *reinterpret_cast<const uint4*>(A + row * lda + col);
+    *reinterpret_cast<uint4*>(stg + stg_off(rr, ch)) = v;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack8(uint4 u, float (&o)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+}
+
+// One warp, 32 rows x 64 columns [col0, col0 + 64): acc = 64 fp32 per thread (its own row).
+template <int EPI>
+__device__ __forceinline__ void epilogue_group64(const GemmDev& p, uint8_t* stg, int row0, int col0,
+                                                 const uint32_t (&r0)[32], const uint32_t (&r1)[32], int lane) {
+  RowMap rm{row0, p.M, p.remap_rows, p.remap_stride, p.remap_offset};
+  const int my_row = row0 + lane;
+  if constexpr (EPI == VDS_EPI_GATE_RES || EPI == VDS_EPI_DGELU) {
+    stg_load(stg, p.aux, p.ldaux, rm, col0, p.N, lane);
+    __syncwarp();
+  }
+  uint4 keep[8];  // first output (bf16 Linear result) kept packed while the second goes through the buffer
+  const int b = (EPI == VDS_EPI_GATE_RES) ? min(my_row, p.M - 1) / p.rows_per_batch : 0;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int col = col0 + g * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]);
+    const bool col_ok = col < p.N;
+    if constexpr (EPI != VDS_EPI_DGELU) {
+      if (p.bias != nullptr && col_ok) {
+        float bb[8];
+        ld8_bf16(p.bias + col, bb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += bb[j];
+      }
+    }
+    uint8_t* slot = stg + stg_off(lane, g);
+    if constexpr (EPI == VDS_EPI_STORE) {
+      *reinterpret_cast<uint4*>(slot) = pack8(acc);
+    } else if constexpr (EPI == VDS_EPI_BIAS_GELU) {
+      float act[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = bf16_round(acc[j]);
+        act[j] = gelu_erf(acc[j]);
+      }
+      keep[g] = pack8(acc);
+      *reinterpret_cast<uint4*>(slot) = pack8(act);
+    } else if constexpr (EPI == VDS_EPI_GATE_RES) {
+      float g8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, x8[8], o8[8];
+      if (col_ok) ld8_bf16(p.gate + (long long)b * p.gate_stride + col, g8);
+      unpack8(*reinterpret_cast<const uint4*>(slot), x8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = bf16_round(acc[j]);                      // Linear output is bf16 in the reference
+        o8[j] = x8[j] + bf16_round(acc[j] * g8[j]);      // x + (out * gate), each op rounded to bf16
+      }
+      keep[g] = pack8(acc);
+      *reinterpret_cast<uint4*>(slot) = pack8(o8);
+    } else if constexpr (EPI == VDS_EPI_DGELU) {
+      float h8[8];
+      unpack8(*reinterpret_cast<const uint4*>(slot), h8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= dgelu_erf(h8[j]);
+      *reinterpret_cast<uint4*>(slot) = pack8(acc);
+    }
+  }
+  __syncwarp();
+  if constexpr (EPI == VDS_EPI_STORE || EPI == VDS_EPI_DGELU) {
+    stg_store(stg, reinterpret_cast<bf16*>(p.C), p.ldc, rm, col0, p.N, lane, EPI == VDS_EPI_STORE);
+  } else {
+    stg_store(stg, reinterpret_cast<bf16*>(p.C2), p.ldc2, rm, col0, p.N, lane, false);
+    if (p.C != nullptr) {
+      __syncwarp();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(stg + stg_off(lane, g)) = keep[g];
+      __syncwarp();
+      stg_store(stg, reinterpret_cast<bf16*>(p.C), p.ldc, rm, col0, p.N, lane, false);
+    }
+  }
+  __syncwarp();
 }
 
 // One thread handles 32 consecutive columns [col0, col0+32) of output row `row`.
@@ -171,7 +312,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
@@ -260,8 +401,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;           // TMEM lane quadrant this warp may access
+    const int chalf = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mt = tile % m_tiles;
@@ -272,16 +414,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       const int row = mt * BM + q * 32 + lane;
       const uint32_t t_base = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      constexpr bool kF32 = (EPI == VDS_EPI_ACCUM_F32 || EPI == VDS_EPI_STORE_F32);
+      if constexpr (kF32) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_base + c * 32, v);
-        tmem_ld_wait();
-        epilogue_row<EPI>(p, row, nt * BN + c * 32, v);
+        for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_base + c * 32, v);
+          tmem_ld_wait();
+          epilogue_row<EPI>(p, row, nt * BN + c * 32, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+      } else {
+        uint8_t* stg = smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + (warp - 2) * 4096;
+        constexpr int GROUPS = BN / 128;   // 64-column groups per warp (its half of the tile)
+#pragma unroll 1
+        for (int gi = 0; gi < GROUPS; ++gi) {
+          const int cg = chalf * GROUPS + gi;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_base + cg * 64, r0);
+          tmem_ld32(t_base + cg * 64 + 32, r1);
+          tmem_ld_wait();
+          if (gi == GROUPS - 1) {          // accumulator fully read: hand it back before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          }
+          epilogue_group64<EPI>(p, stg, mt * BM + q * 32, nt * BN + cg * 64, r0, r1, lane);
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
   }
 
