@@ -188,7 +188,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float alpha = 1.0f;
       const bool need = mxs > m_run + 8.0f;         // lazy: p stays <= 2^8 otherwise
       if (need) {
-        alpha = exp2f(m_run - mxs);                 // 0 on the first tile
+        alpha = ex2(m_run - mxs);                   // 0 on the first tile
         m_run = mxs;
       }
       if (j > 0 && __any_sync(0xffffffffu, need)) {
@@ -213,18 +213,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld32(tS + c * 32, v);
         tmem_ld_wait();
         if (valid >= 128) {
+          float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = exp2f(fmaf(__uint_as_float(v[i]), sl2, nm));
-            const float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), sl2, nm));
-            sum += p0 + p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
+            const float2 x = fma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                                  make_float2(sl2, sl2), make_float2(nm, nm));
+            const float2 pe = make_float2(ex2(x.x), ex2(x.y));
+            s2 = add2(s2, pe);
+            pk[i >> 1] = pack_bf16x2(pe.x, pe.y);
           }
+          sum += s2.x + s2.y;
         } else {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c * 32 + i < valid) ? exp2f(fmaf(__uint_as_float(v[i]), sl2, nm)) : 0.f;
-            const float p1 = (c * 32 + i + 1 < valid) ? exp2f(fmaf(__uint_as_float(v[i + 1]), sl2, nm)) : 0.f;
+            const float p0 = (c * 32 + i < valid) ? ex2(fmaf(__uint_as_float(v[i]), sl2, nm)) : 0.f;
+            const float p1 = (c * 32 + i + 1 < valid) ? ex2(fmaf(__uint_as_float(v[i + 1]), sl2, nm)) : 0.f;
             sum += p0 + p1;
             pk[i >> 1] = pack_bf16x2(p0, p1);
           }
@@ -444,15 +447,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int sc = ct & 63;
       {
         const int q = qt0 * QSUB + sc;
-        s_stat[(ct < 64 ? 0 : 64) + sc] = q < p.Lq ? stat_src[q] : 0.f;
+        s_stat[(ct < 64 ? 0 : 64) + sc] = q < p.Lq ? stat_src[q] * (ct < 64 ? -1.0f : p.scale) : 0.f;
       }
+      const bool kv_full_tile = kv0 + 128 <= p.Lk;
       for (int i = 0; i < n_q; ++i) {
         const int bb = i & 1;
         const int q0 = (qt0 + i) * QSUB;
         float next_stat = 0.f;
         if (i + 1 < n_q) {
           const int q = q0 + QSUB + sc;
-          next_stat = q < p.Lq ? stat_src[q] : 0.f;
+          next_stat = q < p.Lq ? stat_src[q] * (ct < 64 ? -1.0f : p.scale) : 0.f;   // -lse | delta*scale
         }
         named_bar_sync(1, 128);            // stats of this sub-tile visible; previous iteration fully done
         const float* lse_s = s_stat + bb * 128;
@@ -468,19 +472,38 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_ld32(tST + c * 32, sv);
           tmem_ld32(tDPT + c * 32, dv);
           tmem_ld_wait();
+          if (kv_full_tile && qvalid >= QSUB) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float pv[2], ds[2];
+            for (int e = 0; e < 32; e += 4) {
+              const float4 nl = *reinterpret_cast<const float4*>(lse_s + c * 32 + e);
+              const float4 dl = *reinterpret_cast<const float4*>(del_s + c * 32 + e);
+              const float nls[4] = {nl.x, nl.y, nl.z, nl.w}, dls[4] = {dl.x, dl.y, dl.z, dl.w};
+              float pv[4], ds[4];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const int col = c * 32 + e + u;
-              float pr = exp2f(fmaf(__uint_as_float(sv[e + u]), p.scale_log2, -lse_s[col]));
-              pr = (kv_ok && col < qvalid) ? pr : 0.f;
-              pv[u] = pr;
-              ds[u] = pr * (__uint_as_float(dv[e + u]) - del_s[col]) * p.scale;
+              for (int u = 0; u < 4; ++u) {
+                pv[u] = ex2(fmaf(__uint_as_float(sv[e + u]), p.scale_log2, nls[u]));
+                ds[u] = pv[u] * fmaf(__uint_as_float(dv[e + u]), p.scale, -dls[u]);
+              }
+              pp[c * 16 + (e >> 1)] = pack_bf16x2(pv[0], pv[1]);
+              pp[c * 16 + (e >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
+              dd[c * 16 + (e >> 1)] = pack_bf16x2(ds[0], ds[1]);
+              dd[c * 16 + (e >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
             }
-            pp[c * 16 + (e >> 1)] = pack_bf16x2(pv[0], pv[1]);
-            dd[c * 16 + (e >> 1)] = pack_bf16x2(ds[0], ds[1]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              float pv[2], ds[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int col = c * 32 + e + u;
+                float pr = ex2(fmaf(__uint_as_float(sv[e + u]), p.scale_log2, lse_s[col]));
+                pr = (kv_ok && col < qvalid) ? pr : 0.f;
+                pv[u] = pr;
+                ds[u] = pr * fmaf(__uint_as_float(dv[e + u]), p.scale, -del_s[col]);
+              }
+              pp[c * 16 + (e >> 1)] = pack_bf16x2(pv[0], pv[1]);
+              dd[c * 16 + (e >> 1)] = pack_bf16x2(ds[0], ds[1]);
+            }
           }
         }
         if (i > 0) mbar_wait(mma_done + 8 * (bb ^ 1), ((i - 1) >> 1) & 1);   // P^T / dS^T smem consumed
