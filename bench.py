@@ -280,6 +280,9 @@ def run_ours(args):
             cb = cpu_reference_step(args.workload, steps=2, warmup=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
+        if os.environ.get("VDS_BENCH_OUT"):
+            with open(os.environ["VDS_BENCH_OUT"], "a") as f:
+                f.write(json.dumps(line) + "\n")
     if world > 1:
         dist.destroy_process_group()
 

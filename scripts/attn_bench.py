@@ -54,3 +54,25 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def misc():
+    dev = "cuda"
+    B, Lr, h = 2, 8208, 512
+    x = torch.randn((B * Lr, h), device=dev).bfloat16(); dy = torch.randn_like(x); res = torch.randn_like(x)
+    mod = torch.randn((B, 9 * h), device=dev).bfloat16()
+    y, rstd = ops.rmsnorm_mod_fwd(x, B, Lr, h, scale=mod[:, h:2*h], shift=mod[:, :h])
+    dmod = torch.zeros((B, 9 * h), device=dev, dtype=torch.float32)
+    mn, _ = timeit(lambda: ops.rmsnorm_mod_fwd(x, B, Lr, h, scale=mod[:, h:2*h], shift=mod[:, :h]))
+    print(f"rmsnorm_fwd: {mn*1e3:.1f} us ({(2*x.numel()*2)/mn/1e6:.0f} GB/s)")
+    mn, _ = timeit(lambda: ops.rmsnorm_mod_bwd(dy, x, rstd, B, Lr, h, scale=mod[:, h:2*h], dx_res=res, dscale=dmod[:, h:2*h], dshift=dmod[:, :h]))
+    print(f"rmsnorm_bwd: {mn*1e3:.1f} us ({(4*x.numel()*2)/mn/1e6:.0f} GB/s)")
+    mn, _ = timeit(lambda: ops.gate_bwd(dy, x, mod[:, 2*h:3*h], dmod[:, 2*h:3*h], B, Lr, h))
+    print(f"gate_bwd: {mn*1e3:.1f} us ({(3*x.numel()*2)/mn/1e6:.0f} GB/s)")
+    big = torch.randn((B * Lr, 4 * h), device=dev).bfloat16(); o = torch.zeros(4 * h, device=dev)
+    mn, _ = timeit(lambda: ops.colsum(big, o))
+    print(f"colsum 4h: {mn*1e3:.1f} us ({big.numel()*2/mn/1e6:.0f} GB/s)")
+
+
+if __name__ == "__main__":
+    misc()

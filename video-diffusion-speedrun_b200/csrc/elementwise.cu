@@ -14,6 +14,10 @@ __device__ __forceinline__ void ld8(const bf16* p, float (&o)[8]) {
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
 }
+__device__ __forceinline__ void unpack8f(uint4 u, float (&o)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+}
 __device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
@@ -212,26 +216,49 @@ struct NormBwdArgs {
   int dx_full_rows;  // 1: dx indexed like x (in rows); rows outside the normed range untouched
 };
 
-template <int NV>
+template <int NV, bool HAS_W>
 __global__ void __launch_bounds__(256) rmsnorm_mod_bwd_kernel(const NormBwdArgs a) {
+  constexpr bool PF = false;  // one-row-ahead prefetch costs more in occupancy than it buys (measured)
   extern __shared__ float red[];  // [8 warps][3][h] would be too big: reduce sequentially below
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * a.rows_per_cta;
   const int r1 = min(a.rows_per_batch_out, r0 + a.rows_per_cta);
   const int ng = a.h / 8;
-  float acc_sc[NV][8], acc_sh[NV][8], acc_w[NV][8];
+  float acc_sc[NV][8], acc_sh[NV][8], acc_w[HAS_W ? NV : 1][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc_sc[i][j] = 0.f; acc_sh[i][j] = 0.f; acc_w[i][j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { acc_sc[i][j] = 0.f; acc_sh[i][j] = 0.f; if (HAS_W) acc_w[HAS_W ? i : 0][j] = 0.f; }
 
-  for (int r = r0 + warp; r < r1; r += 8) {
+  // one row per warp per step, the next row's 16-byte groups are already in flight (raw registers)
+  uint4 nx[NV], ndy[NV], nrs[NV];
+  float nrstd = 0.f;
+  auto fetch = [&](int r) {
     const long long orow = (long long)b * a.rows_per_batch_out + r;
     const long long irow = (long long)b * a.in_batch_stride + a.in_row_offset + r;
-    const float rstd = a.rstd[orow];
-    const bf16* xr = a.x + irow * a.h;
-    const bf16* dyr = a.dy + orow * a.h;
+    const long long drow = a.dx_full_rows ? irow : orow;
+    nrstd = a.rstd[orow];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i * 32 + lane < ng) {
+        const int c = (i * 32 + lane) * 8;
+        nx[i] = *reinterpret_cast<const uint4*>(a.x + irow * a.h + c);
+        ndy[i] = *reinterpret_cast<const uint4*>(a.dy + orow * a.h + c);
+        if (a.dx_res != nullptr) nrs[i] = *reinterpret_cast<const uint4*>(a.dx_res + drow * a.h + c);
+      }
+    }
+  };
+  if (PF && r0 + warp < r1) fetch(r0 + warp);
+  for (int r = r0 + warp; r < r1; r += 8) {
+    if (!PF) fetch(r);
+    const long long orow = (long long)b * a.rows_per_batch_out + r;
+    const long long irow = (long long)b * a.in_batch_stride + a.in_row_offset + r;
+    const float rstd = nrstd;
+    uint4 cx[NV], cdy[NV], crs[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { cx[i] = nx[i]; cdy[i] = ndy[i]; crs[i] = nrs[i]; }
+    if (PF && r + 8 < r1) fetch(r + 8);
     float dxn[NV][8], xn[NV][8];
     float dot = 0.f;
 #pragma unroll
@@ -239,15 +266,15 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_bwd_kernel(const NormBwdArgs 
       if (i * 32 + lane < ng) {
         const int c = (i * 32 + lane) * 8;
         float xv[8], dyv[8], w[8], sc[8];
-        ld8(xr + c, xv);
-        ld8(dyr + c, dyv);
-        if (a.weight != nullptr) ld8(a.weight + c, w);
+        unpack8f(cx[i], xv);
+        unpack8f(cdy[i], dyv);
+        if (HAS_W) ld8(a.weight + c, w);
         if (a.scale != nullptr) ld8(a.scale + (long long)b * a.mod_stride + c, sc);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float n = xv[j] * rstd;
           xn[i][j] = n;
-          const float xhat = bf16_round(a.weight != nullptr ? n * w[j] : n);
+          const float xhat = bf16_round(HAS_W ? n * w[j] : n);
           float dxhat = dyv[j];
           if (a.scale != nullptr) {
             acc_sc[i][j] += dyv[j] * xhat;
@@ -255,8 +282,8 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_bwd_kernel(const NormBwdArgs 
             dxhat = dyv[j] * bf16_round(1.0f + sc[j]);
           }
           float d = dxhat;
-          if (a.weight != nullptr) {
-            acc_w[i][j] += dxhat * n;
+          if (HAS_W) {
+            acc_w[HAS_W ? i : 0][j] += dxhat * n;
             d = dxhat * w[j];
           }
           dxn[i][j] = d;
@@ -275,7 +302,7 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_bwd_kernel(const NormBwdArgs 
         for (int j = 0; j < 8; ++j) o[j] = rstd * (dxn[i][j] - xn[i][j] * dot);
         if (a.dx_res != nullptr) {
           float rr[8];
-          ld8(a.dx_res + drow * a.h + c, rr);
+          unpack8f(crs[i], rr);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += rr[j];
         }
@@ -283,26 +310,32 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_bwd_kernel(const NormBwdArgs 
       }
     }
   }
-  // column sums: warps take turns through shared memory (8 warps x h floats per quantity)
-  float* s = red;  // [h]
+  // column sums: every warp parks its register partials in shared memory (conflict-free [j][group] order), the
+  // CTA adds the 8 warps and issues ONE global atomicAdd per column.
+  float* s = red;  // [8 warps][h]
+  const int ngr = a.h / 8;
   for (int q = 0; q < 3; ++q) {
     if (q < 2 && a.scale == nullptr) continue;
-    if (q == 2 && a.weight == nullptr) continue;
-    for (int i = threadIdx.x; i < a.h; i += blockDim.x) s[i] = 0.f;
-    __syncthreads();
+    if (q == 2 && !HAS_W) continue;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      if (i * 32 + lane < ng) {
-        const int c = (i * 32 + lane) * 8;
+      const int g = i * 32 + lane;
+      if (g < ngr) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          atomicAdd(&s[c + j], q == 0 ? acc_sc[i][j] : (q == 1 ? acc_sh[i][j] : acc_w[i][j]));
+          s[warp * a.h + j * ngr + g] = q == 0 ? acc_sc[i][j] : (q == 1 ? acc_sh[i][j] : acc_w[HAS_W ? i : 0][j]);
       }
     }
     __syncthreads();
     float* dst = q == 0 ? a.dscale + (long long)b * a.dmod_stride
                         : (q == 1 ? a.dshift + (long long)b * a.dmod_stride : a.dweight);
-    for (int i = threadIdx.x; i < a.h; i += blockDim.x) atomicAdd(&dst[i], s[i]);
+    for (int col = threadIdx.x; col < a.h; col += blockDim.x) {   // consecutive threads -> consecutive addresses
+      const int pos = (col & 7) * ngr + (col >> 3);
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s[w * a.h + pos];
+      atomicAdd(&dst[col], t);
+    }
     __syncthreads();
   }
 }
@@ -330,15 +363,32 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   }
-  for (int r = r0 + warp; r < r1; r += 8) {
+  uint4 ndx[NV], no[NV];
+  auto fetch = [&](int r) {
     const long long row = (long long)b * a.rows_per_batch + r;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       if (i * 32 + lane < ng) {
         const int c = (i * 32 + lane) * 8;
+        ndx[i] = *reinterpret_cast<const uint4*>(a.dx + row * a.h + c);
+        no[i] = *reinterpret_cast<const uint4*>(a.o + row * a.h + c);
+      }
+    }
+  };
+  if (r0 + warp < r1) fetch(r0 + warp);
+  for (int r = r0 + warp; r < r1; r += 8) {
+    const long long row = (long long)b * a.rows_per_batch + r;
+    uint4 cdx[NV], co[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { cdx[i] = ndx[i]; co[i] = no[i]; }
+    if (r + 8 < r1) fetch(r + 8);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i * 32 + lane < ng) {
+        const int c = (i * 32 + lane) * 8;
         float dxv[8], ov[8], out[8];
-        ld8(a.dx + row * a.h + c, dxv);
-        ld8(a.o + row * a.h + c, ov);
+        unpack8f(cdx[i], dxv);
+        unpack8f(co[i], ov);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           acc[i][j] += dxv[j] * ov[j];
@@ -348,19 +398,23 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
       }
     }
   }
-  for (int i = threadIdx.x; i < a.h; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
+  const int ngr = a.h / 8;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    if (i * 32 + lane < ng) {
-      const int c = (i * 32 + lane) * 8;
+    const int g = i * 32 + lane;
+    if (g < ngr) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&red[c + j], acc[i][j]);
+      for (int j = 0; j < 8; ++j) red[warp * a.h + j * ngr + g] = acc[i][j];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < a.h; i += blockDim.x)
-    atomicAdd(&a.dgate[(long long)b * a.dgate_stride + i], red[i]);
+  for (int col = threadIdx.x; col < a.h; col += blockDim.x) {
+    const int pos = (col & 7) * ngr + (col >> 3);
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w * a.h + pos];
+    atomicAdd(&a.dgate[(long long)b * a.dgate_stride + col], t);
+  }
 }
 
 // ------------------------------------------------------------------------------------- QKV post (fwd)
@@ -669,11 +723,21 @@ int vds_rmsnorm_mod_bwd(const void* dy, const void* x, const float* rstd, const 
   a.in_row_offset = in_row_offset; a.dx_full_rows = dx_full_rows;
   // ~2 waves of CTAs over the chip, at least 8 rows (one per warp) each
   int chunks = max(1, (2 * num_sms()) / max(1, B));
-  a.rows_per_cta = max(8, ceil_div(rows_per_batch_out, chunks));
+  a.rows_per_cta = max(16, ceil_div(rows_per_batch_out, chunks));
   dim3 grid(ceil_div(rows_per_batch_out, a.rows_per_cta), B);
   const int nvn = (h + 255) / 256;
-#define VDS_L(NVV) rmsnorm_mod_bwd_kernel<NVV><<<grid, 256, h * sizeof(float), (cudaStream_t)stream>>>(a)
-  if (nvn <= 2) VDS_L(2); else if (nvn <= 3) VDS_L(3); else if (nvn <= 5) VDS_L(5); else VDS_L(8);
+#define VDS_L(NVV, HW)                                                                                      \
+  do {                                                                                                     \
+    if (8 * h * sizeof(float) > 48 * 1024)                                                                 \
+      cudaFuncSetAttribute(rmsnorm_mod_bwd_kernel<NVV, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                           (int)(8 * h * sizeof(float)));                                                  \
+    rmsnorm_mod_bwd_kernel<NVV, HW><<<grid, 256, 8 * h * sizeof(float), (cudaStream_t)stream>>>(a);        \
+  } while (0)
+  if (weight != nullptr) {
+    if (nvn <= 2) VDS_L(2, true); else if (nvn <= 3) VDS_L(3, true); else if (nvn <= 5) VDS_L(5, true); else VDS_L(8, true);
+  } else {
+    if (nvn <= 2) VDS_L(2, false); else if (nvn <= 3) VDS_L(3, false); else if (nvn <= 5) VDS_L(5, false); else VDS_L(8, false);
+  }
 #undef VDS_L
   VDS_CHECK_LAUNCH("rmsnorm_mod_bwd");
   return VDS_OK;
@@ -686,10 +750,16 @@ int vds_gate_bwd(const void* dx, const void* o, const void* gate, void* d_o, flo
   a.dx = (const bf16*)dx; a.o = (const bf16*)o; a.gate = (const bf16*)gate; a.d_o = (bf16*)d_o; a.dgate = dgate;
   a.gate_stride = gate_stride; a.dgate_stride = dgate_stride; a.h = h; a.rows_per_batch = rows_per_batch;
   int chunks = max(1, (2 * num_sms()) / max(1, B));
-  a.rows_per_cta = max(8, ceil_div(rows_per_batch, chunks));
+  a.rows_per_cta = max(16, ceil_div(rows_per_batch, chunks));
   dim3 grid(ceil_div(rows_per_batch, a.rows_per_cta), B);
   const int nvn = (h + 255) / 256;
-#define VDS_L(NVV) gate_bwd_kernel<NVV><<<grid, 256, h * sizeof(float), (cudaStream_t)stream>>>(a)
+#define VDS_L(NVV)                                                                                         \
+  do {                                                                                                     \
+    if (8 * h * sizeof(float) > 48 * 1024)                                                                 \
+      cudaFuncSetAttribute(gate_bwd_kernel<NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                           (int)(8 * h * sizeof(float)));                                                  \
+    gate_bwd_kernel<NVV><<<grid, 256, 8 * h * sizeof(float), (cudaStream_t)stream>>>(a);                   \
+  } while (0)
   if (nvn <= 2) VDS_L(2); else if (nvn <= 3) VDS_L(3); else if (nvn <= 5) VDS_L(5); else VDS_L(8);
 #undef VDS_L
   VDS_CHECK_LAUNCH("gate_bwd");
