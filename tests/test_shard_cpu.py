@@ -1,0 +1,128 @@
+"""Host-side logic of the parameter sharding (apply_fsdp replacement): layout math and, with a real
+world_size-2 gloo process group on CPU, the all-gather / reduce-scatter plumbing and state_dict assembly."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+CFG = dict(in_channels=16, patch_size=2, time_patch_size=2, hidden_size=64, depth=3, num_heads=2, mlp_ratio=4.0,
+           cross_attn_input_size=32, residual_v=True, train_bias_and_rms=True, use_rope=True)
+
+
+def _shapes():
+    import vds_b200  # noqa: F401
+    from vds_b200.model import DiT
+    torch.manual_seed(0)
+    m = DiT(**CFG)
+    return m, [(n, tuple(p.shape)) for n, p in m.named_parameters()]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_layout_covers_every_parameter_exactly_once(world):
+    from vds_b200.shard import ALIGN, Layout
+    m, shapes = _shapes()
+    lay = Layout(shapes, CFG["depth"], world)
+    assert len(lay.groups) == CFG["depth"] + 1 and lay.full_total == sum(lay.group_numel)
+    for g, n in enumerate(lay.group_numel):
+        assert n % (ALIGN * world) == 0
+    total = 0
+    for name, shape in shapes:
+        g, off, numel, shp = lay.param[name]
+        assert off % ALIGN == 0 and shp == shape
+        pieces = [lay.shard_range(name, r) for r in range(world)]
+        assert sum(p[2] for p in pieces) == numel                      # ranks tile the parameter
+        pos = 0
+        for s, po, ln in pieces:
+            if ln:
+                assert po == pos
+                pos += ln
+        total += numel
+    assert total == sum(p.numel() for p in m.parameters())
+    # AdamW chunk tables: disjoint, inside the shard, cover exactly the owned elements, right group ids
+    group_of = {n: (i % 5) for i, (n, _) in enumerate(shapes)}
+    for r in range(world):
+        st, ln, gid = lay.adam_chunks(r, group_of, chunk=1000)
+        covered = torch.zeros(lay.shard_total, dtype=torch.int32)
+        for s, l, g in zip(st, ln, gid):
+            covered[s:s + l] += 1
+        assert covered.max().item() <= 1
+        assert covered.sum().item() == sum(lay.shard_range(n, r)[2] for n, _ in shapes)
+        for n, _ in shapes:
+            s, _, l = lay.shard_range(n, r)
+            hits = [g for s2, l2, g in zip(st, ln, gid) if s <= s2 < s + l]
+            assert all(h == group_of[n] for h in hits)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import vds_b200  # noqa: F401
+        from vds_b200.model import DiT, apply_fsdp
+        torch.manual_seed(0)
+        m = DiT(**CFG)
+        ref = {n: p.detach().clone() for n, p in m.named_parameters()}
+        names = list(ref)
+        m = apply_fsdp(m, torch.bfloat16, torch.float32)
+        flat = m._flat
+        assert flat.world == world and flat.rank == rank
+        assert [n for n, _ in m.named_parameters()] == names               # names preserved (get_mup_setup relies on it)
+        # 1. gathered bf16 compute parameters == bf16 image of the full parameters
+        P = flat.compute_params()
+        for n in names:
+            assert torch.equal(P[n], ref[n].to(torch.bfloat16)), n
+        # 2. local parameters are this rank's slice of the flat fp32 master
+        for n, p in m.named_parameters():
+            s, po, ln = flat.layout.shard_range(n, rank)
+            assert p.numel() == ln and torch.equal(p.detach().flatten(), ref[n].flatten()[po:po + ln])
+        # 3. fp32 reduce-scatter averages rank-dependent gradients
+        flat.begin_backward()
+        for n in names:
+            flat.grad_views[n].copy_(ref[n] * (rank + 1))
+        for g in range(flat.depth):
+            flat.block_backward_done(g)
+        flat.end_backward()
+        mean = sum(range(1, world + 1)) / world
+        for n, p in m.named_parameters():
+            if n == "blocks.0.lambda_param":
+                assert p.grad is None
+                continue
+            s, po, ln = flat.layout.shard_range(n, rank)
+            assert torch.allclose(p.grad.flatten(), ref[n].flatten()[po:po + ln] * mean, rtol=1e-6, atol=1e-7), n
+        # 4. state_dict() returns full reference-shaped tensors
+        sd = m.state_dict()
+        for n in names:
+            assert sd[n].shape == ref[n].shape and torch.equal(sd[n].cpu(), ref[n]), n
+        # 5. get_mup_setup works on the sharded module (full shapes from paramstatus)
+        groups, settings = m.get_mup_setup(1e-3, 1e-1, ["patch_proj", "context_kv", "positional_embedding"])
+        assert sum(len(g["params"]) for g in groups) == len(names)
+        out.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_allgather_reducescatter_statedict():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", f"rank {rank}: {msg}"
