@@ -116,45 +116,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, false, true);
-      auto issue_s = [&](int t, int s) {   // S_t = Q_t K[s]^T
+    // whole warp runs the (warp-uniform) control flow; one elected lane issues MMAs + commits
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, false, false);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, false, true);
+    auto issue_s = [&](int t, int s) {   // S_t = Q_t K[s]^T   (called by the elected lane only)
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16(tmem + t * 128, desc_kmajor(sQ + t * TILE_BYTES, kk), desc_kmajor(sK + s * TILE_BYTES, kk),
-                    idesc_qk, kk > 0);
-        umma_commit(s_full + 8 * t);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full, 0);
-      tc_fence_after();
+      for (int kk = 0; kk < 8; ++kk)
+        umma_bf16(tmem + t * 128, desc_kmajor(sQ + t * TILE_BYTES, kk), desc_kmajor(sK + s * TILE_BYTES, kk),
+                  idesc_qk, kk > 0);
+      umma_commit(s_full + 8 * t);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(k_full, 0);
+    tc_fence_after();
+    if (elect_one()) {
       issue_s(0, 0);
       issue_s(1, 0);
       umma_commit(k_empty);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        mbar_wait(v_full + 8 * s, (j >> 1) & 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j & 1;
+      mbar_wait(v_full + 8 * s, (j >> 1) & 1);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(p_full + 8 * t, j & 1);
-          tc_fence_after();
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(p_full + 8 * t, j & 1);
+        if (t == 0 && j + 1 < n_kv) mbar_wait(k_full + 8 * (s ^ 1), ((j + 1) >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)   // O_t += P_t V : A = P (bf16, TMEM, 8 columns per k-step)
             umma_bf16_ts(tmem + 256 + t * 128, tmem + t * 128 + kk * 8, desc_mnmajor(sV + s * TILE_BYTES, kk),
                          idesc_pv, (j > 0 || kk > 0));
           if (t == 1) umma_commit(v_empty + 8 * s);
           if (j + 1 < n_kv) {
-            if (t == 0) {
-              mbar_wait(k_full + 8 * (s ^ 1), ((j + 1) >> 1) & 1);
-              tc_fence_after();
-            }
             issue_s(t, s ^ 1);
             if (t == 1) umma_commit(k_empty + 8 * (s ^ 1));
           } else {
             umma_commit(o_done + 8 * t);
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -293,6 +295,7 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __r
 
 struct AttnBwdParams {
   const float* lse; const float* delta;   // [B, nh, Lq]
+  float* dq_acc; long long lddq;           // fp32 [B, Lq, lddq] (+=)
   bf16* dk; long long lddk;                // bf16 [B, Lk, lddk], head at head*128 (q_splits == 1)
   bf16* dv; long long lddv;
   float* dk_acc; float* dv_acc; long long ldkv_acc;  // fp32 accumulation targets when q_splits > 1
@@ -390,15 +393,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);     // S^T, dP^T
-        constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, false, true);   // dV, dK
-        constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, true, true);      // dQ^T
-        auto issue_sdp = [&](int k) {
-          const int bb = k & 1, st = k % 3;
-          mbar_wait(qdo_full + 8 * st, (k / 3) & 1);
-          if (k >= 2) mbar_wait(dq_drained + 8 * bb, ((k >> 1) - 1) & 1);
-          tc_fence_after();
+      // The whole warp runs the control flow (warp-uniform => descriptors stay in uniform registers and the
+      // UTCHMMA issue needs no per-lane waterfall); one elected lane issues the MMAs and their commits.
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);     // S^T, dP^T
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, false, true);   // dV, dK
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, true, true);      // dQ^T
+      auto issue_sdp = [&](int k) {
+        const int bb = k & 1, st = k % 3;
+        mbar_wait(qdo_full + 8 * st, (k / 3) & 1);
+        if (k >= 2) mbar_wait(dq_drained + 8 * bb, ((k >> 1) - 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
           const uint32_t q = sQ + st * 2 * QT_BYTES, d_o = q + QT_BYTES;
           const uint32_t tST = tmem + 256 + bb * 128, tDPT = tST + 64;
 #pragma unroll
@@ -410,14 +415,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_bf16(tDPT, desc_kmajor(sV, kk), umma_smem_desc(d_o + (kk >> 2) * QT_HALF + (kk & 3) * 32, 16, 1024),
                       idesc_s, kk > 0);
           umma_commit(sdp_full + 8 * bb);
-        };
-        mbar_wait(kv_full, 0);
-        issue_sdp(0);
-        for (int i = 0; i < n_q; ++i) {
-          const int bb = i & 1, st = i % 3;
-          if (i + 1 < n_q) issue_sdp(i + 1);
-          mbar_wait(pds_full, i & 1);
-          tc_fence_after();
+        }
+        __syncwarp();
+      };
+      mbar_wait(kv_full, 0);
+      issue_sdp(0);
+      for (int i = 0; i < n_q; ++i) {
+        const int bb = i & 1, st = i % 3;
+        if (i + 1 < n_q) issue_sdp(i + 1);
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+        if (elect_one()) {
           const uint32_t q = sQ + st * 2 * QT_BYTES, d_o = q + QT_BYTES;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)   // dV += P^T dO : A = P^T [128 x 64] K-major, B = dO MN-major (N = d)
@@ -434,6 +442,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_commit(qdo_empty + 8 * st);
           umma_commit(mma_done + 8 * bb);
         }
+        __syncwarp();
       }
     } else if (warp >= 4 && warp < 8) {
       // ------------------------------------------------------------ compute warpgroup (thread == kv row)
@@ -674,7 +683,7 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
     VDS_CHECK_LAUNCH("attn_bwd_prep");
   }
   AttnBwdParams p;
-  p.lse = lse; p.delta = delta;
+  p.lse = lse; p.delta = delta; p.dq_acc = dq_acc; p.lddq = lddq;
   p.dk = (bf16*)dk; p.lddk = lddk; p.dv = (bf16*)dv; p.lddv = lddv;
   p.dk_acc = dk_acc; p.dv_acc = dv_acc; p.ldkv_acc = ldkv_acc;
   p.Lq = Lq; p.Lk = Lk; p.nh = nh; p.q_splits = q_splits;

@@ -366,24 +366,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int rest = tile / m_tiles;
-        const int sp = rest / n_tiles;
-        const int kb0 = sp * p.k_per_split;
-        const int kb1 = min(k_iters, kb0 + p.k_per_split);
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+    // warp-uniform control flow (all lanes wait on the barriers), one elected lane issues MMAs + commits
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int rest = tile / m_tiles;
+      const int sp = rest / n_tiles;
+      const int kb0 = sp * p.k_per_split;
+      const int kb1 = min(k_iters, kb0 + p.k_per_split);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t a_addr = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
 #pragma unroll
@@ -395,9 +396,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (kb == kb1 - 1) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
