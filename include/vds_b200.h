@@ -74,6 +74,7 @@ typedef struct vds_gemm_args {
    * tokens (model.py:362) without a concat copy. */
   int32_t remap_rows, remap_stride, remap_offset;
   int32_t tile_n; /* 0 = automatic (128 or 256), 128 = force 128-wide tiles (tuning / tests) */
+  int32_t cluster; /* 2 = 2-CTA clusters with the B tile multicast to both CTAs (opt-in; no gain measured on B200) */
 } vds_gemm_args;
 
 int vds_gemm(const vds_gemm_args* args, void* stream);

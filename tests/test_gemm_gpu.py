@@ -123,3 +123,18 @@ def test_gemm_wide_tiles_epilogues(cuda_dev, tile_n):
     hh = pre.float().requires_grad_(True)
     torch.nn.functional.gelu(hh).backward(dy.float() @ w2.float())
     _close(dh, hh.grad)
+
+
+@pytest.mark.parametrize("cluster", [0, 2])
+@pytest.mark.parametrize("M,N,K", [(304, 256, 512), (16416, 1536, 512), (1296, 512, 2048)])
+def test_gemm_cluster_multicast_matches(cuda_dev, M, N, K, cluster):
+    """2-CTA clusters with multicast B (auto) vs plain launch; odd numbers of m-tiles leave one CTA of a pair idle."""
+    from vds_b200 import ops, lib
+    a, b, bias = _mk((M, K), cuda_dev, 40), _mk((N, K), cuda_dev, 41), _mk((N,), cuda_dev, 42)
+    _close(ops.gemm(a, b, bias=bias, cluster=cluster), a.float() @ b.float().t() + bias.float())
+    dy, w = _mk((M, K), cuda_dev, 43), _mk((K, N), cuda_dev, 44)
+    _close(ops.gemm(dy, w, b_mn=True, cluster=cluster), dy.float() @ w.float())
+    g1, g2 = _mk((K, M), cuda_dev, 45), _mk((K, N), cuda_dev, 46)
+    out = torch.zeros((M, N), device=cuda_dev, dtype=torch.float32)
+    ops.gemm(g1, g2, a_mn=True, b_mn=True, epilogue=lib.EPI_ACCUM_F32, out=out, splits=2, cluster=cluster)
+    _close(out, g1.float().t() @ g2.float())

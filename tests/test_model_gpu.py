@@ -120,3 +120,42 @@ def test_forward_only_and_eval(cuda_dev):
                             rope_starts=starts, table_dtype=torch.bfloat16)
     assert out.dtype == torch.bfloat16 and out.shape == latent.shape
     assert (out.float() - ref).abs().max().item() <= 3e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("hidden,heads,latent_thw,B", [(768, 6, (2, 32, 32), 4), (1152, 9, (4, 16, 16), 2)])
+def test_dit_b_and_xl_widths_vs_oracle(cuda_dev, hidden, heads, latent_thw, B):
+    """BASELINE configs 3/4: DiT-B (768, 6 heads) and DiT-XL (1152, 9 heads) widths at reduced depth / latent size."""
+    cfg = dict(in_channels=16, patch_size=2, time_patch_size=2, hidden_size=hidden, depth=2, num_heads=heads,
+               mlp_ratio=4.0, cross_attn_input_size=4096, residual_v=True, train_bias_and_rms=False, use_rope=True)
+    model = build_model(cfg, 0, 1).to(cuda_dev)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 2 and not any(z in n for z in O.ZERO_INIT):
+                p.mul_(0.1)
+    latent, noise, context, t = [a.to(cuda_dev) for a in O.make_inputs(cfg, B, latent_thw, 512, 4096, 6)]
+    loss, _, grads = _cuda_step(model, latent, noise, context, t, 91, fused=True)
+    thw = tuple(d // 2 for d in latent_thw)
+    rl, _, rg = _oracle_step(model, cfg, latent, noise, context, t, 91, thw, torch.float32, cuda_dev)
+    _compare(f"h={hidden}", loss, grads, rl, rg)
+
+
+def test_sampling_width_forward_only(cuda_dev):
+    """sample.py:43-53 model width (2048, 16 heads), bf16 module + bf16 RoPE tables, forward only, depth reduced."""
+    cfg = dict(in_channels=16, patch_size=2, time_patch_size=2, hidden_size=2048, depth=2, num_heads=16,
+               mlp_ratio=4.0, cross_attn_input_size=4096, residual_v=True, train_bias_and_rms=False, use_rope=True)
+    model = build_model(cfg, 0, 1)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 2 and not any(z in n for z in O.ZERO_INIT):
+                p.mul_(0.1)
+    model = model.to(cuda_dev, torch.bfloat16).eval()
+    latent, noise, context, t = [a.to(cuda_dev) for a in O.make_inputs(cfg, 1, (4, 16, 16), 512, 4096, 7)]
+    with torch.no_grad():
+        torch.manual_seed(5)
+        out = model(latent, context, t)
+        P = {k: v.float() for k, v in params_of(model, device=cuda_dev).items()}
+        torch.manual_seed(5)
+        starts = O.draw_rope_starts((2, 8, 8))
+        ref = O.dit_forward(P, cfg, latent.float(), context.float(), t.float(), rope_starts=starts,
+                            table_dtype=torch.bfloat16)
+    assert (out.float() - ref).abs().max().item() <= 3e-2 * ref.abs().max().item()

@@ -283,7 +283,7 @@ __device__ __forceinline__ void epilogue_row(const GemmDev& p, int row, int col0
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
   using Cfg = GemmCfg<BN>;
@@ -308,7 +308,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);   // every CTA of the cluster releases the slot (its B half is multicast)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -321,21 +321,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
 
-  const int m_tiles = (p.M + BM - 1) / BM;
+  // CL == 2: the two CTAs of a cluster work on vertically adjacent tiles (same n-block, m-blocks 2p and 2p+1) in
+  // lockstep; each loads its own A tile and HALF of the shared B tile, multicast into both CTAs' shared memory,
+  // which cuts the L2 -> SM operand traffic per CTA from A+B to A+B/2 (the K<=2048 GEMMs here are L2-bound).
+  const int m_tiles_real = (p.M + BM - 1) / BM;
+  const int m_tiles = (CL > 1) ? ((m_tiles_real + CL - 1) / CL) : m_tiles_real;   // in units of cluster rows
   const int n_tiles = (p.N + BN - 1) / BN;
   const int k_iters = (p.K + BK - 1) / BK;
   const int total_tiles = m_tiles * n_tiles * p.splits;
+  const int tile0 = blockIdx.x / CL, tile_step = gridDim.x / CL;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile % m_tiles;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int mt = (tile % m_tiles) * CL + crank;
         const int rest = tile / m_tiles;
         const int nt = rest % n_tiles;
         const int sp = rest / n_tiles;
@@ -353,12 +360,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int i = 0; i < BM / 64; ++i)
               tma_load_2d(a_dst + i * (BK * 128), &tmA, full_bar(stage), mt * BM + i * 64, kb * BK);
           }
-          if constexpr (!B_MN) {
-            tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, nt * BN);
-          } else {
+          if constexpr (CL == 1) {
+            if constexpr (!B_MN) {
+              tma_load_2d(b_dst, &tmB, full_bar(stage), kb * BK, nt * BN);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(b_dst + i * (BK * 128), &tmB, full_bar(stage), nt * BN + i * 64, kb * BK);
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_2d(b_dst + i * (BK * 128), &tmB, full_bar(stage), nt * BN + i * 64, kb * BK);
+            }
+          } else {
+            constexpr uint16_t kMask = (1u << CL) - 1;
+            if constexpr (!B_MN) {   // this CTA fetches rows [crank*BN/2, +BN/2) of the B tile for both CTAs
+              tma_load_2d_mc(b_dst + crank * (BN / 2) * 128, &tmB, full_bar(stage), kb * BK,
+                             nt * BN + crank * (BN / 2), kMask);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i) {
+                const int bi = crank * (BN / 128) + i;
+                tma_load_2d_mc(b_dst + bi * (BK * 128), &tmB, full_bar(stage), nt * BN + bi * 64, kb * BK, kMask);
+              }
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -371,7 +392,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int rest = tile / m_tiles;
       const int sp = rest / n_tiles;
       const int kb0 = sp * p.k_per_split;
@@ -395,7 +416,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                         : umma_smem_desc(b_addr + k * 32, 16, 1024);
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          if constexpr (CL == 1) umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          else umma_commit_mc(empty_bar(stage), (1u << CL) - 1);   // ... in BOTH CTAs (the peer multicasts into it)
           if (kb == kb1 - 1) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
         }
         __syncwarp();
@@ -407,8 +429,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int q = warp & 3;           // TMEM lane quadrant this warp may access
     const int chalf = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int mt = tile % m_tiles;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+      const int mt = (tile % m_tiles) * CL + crank;
       const int nt = (tile / m_tiles) % n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
@@ -451,10 +473,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // nobody exits while the peer may still multicast / arrive here
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, int CL = 1>
 static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap tmA, tmB;
@@ -466,7 +489,7 @@ static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
     strides[0] = (uint64_t)a.lda * 2;
     int r = encode_tmap_bf16(&tmA, a.A, 2, dims, strides, box);
     if (r) return r;
-    if (!B_MN) { dims[0] = a.K; dims[1] = a.N; box[0] = BK; box[1] = BN; }
+    if (!B_MN) { dims[0] = a.K; dims[1] = a.N; box[0] = BK; box[1] = BN / CL; }
     else       { dims[0] = a.N; dims[1] = a.K; box[0] = 64; box[1] = BK; }
     strides[0] = (uint64_t)a.ldb * 2;
     r = encode_tmap_bf16(&tmB, a.B, 2, dims, strides, box);
@@ -486,7 +509,7 @@ static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
   p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
   p.remap_rows = a.remap_rows; p.remap_stride = a.remap_stride; p.remap_offset = a.remap_offset;
 
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -496,10 +519,31 @@ static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
     }
     attr_set = true;
   }
-  const int m_tiles = (a.M + BM - 1) / BM, n_tiles = (a.N + BN - 1) / BN;
-  const long long total = (long long)m_tiles * n_tiles * p.splits;
-  const int grid = (int)(total < num_sms() ? total : num_sms());
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  const int m_tiles = ((a.M + BM - 1) / BM + CL - 1) / CL, n_tiles = (a.N + BN - 1) / BN;
+  const long long total = (long long)m_tiles * n_tiles * p.splits;   // cluster-tiles
+  const int max_clusters = num_sms() / CL;
+  const int grid = (int)(total < max_clusters ? total : max_clusters) * CL;
+  if constexpr (CL == 1) {
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+    if (e != cudaSuccess) {
+      set_error("gemm: cluster launch failed: %s", cudaGetErrorString(e));
+      return VDS_ERR_CUDA;
+    }
+  }
   VDS_CHECK_LAUNCH("gemm");
   return VDS_OK;
 }
@@ -509,16 +553,20 @@ static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
 template <bool A_MN, bool B_MN, int EPI>
 static int launch_bn(const vds_gemm_args& a, cudaStream_t s) {
   const long long tiles256 = (long long)((a.M + BM - 1) / BM) * (a.N / 256);
-  if (a.N % 256 == 0 && tiles256 >= num_sms() && a.tile_n != 128) return launch_gemm<256, A_MN, B_MN, EPI>(a, s);
-  return launch_gemm<128, A_MN, B_MN, EPI>(a, s);
+  const bool cluster_ok = (a.M + BM - 1) / BM >= 2 && a.cluster == 2;   // opt-in: measured no gain on B200 (TMA multicast does not dedup L2 reads at cluster size 2)
+  if (a.N % 256 == 0 && tiles256 >= num_sms() && a.tile_n != 128)
+    return cluster_ok ? launch_gemm<256, A_MN, B_MN, EPI, 2>(a, s) : launch_gemm<256, A_MN, B_MN, EPI, 1>(a, s);
+  return cluster_ok ? launch_gemm<128, A_MN, B_MN, EPI, 2>(a, s) : launch_gemm<128, A_MN, B_MN, EPI, 1>(a, s);
 }
 
 template <bool A_MN, bool B_MN>
 static int dispatch_epi(const vds_gemm_args& a, cudaStream_t s) {
   switch (a.epilogue) {
     case VDS_EPI_STORE: return launch_bn<A_MN, B_MN, VDS_EPI_STORE>(a, s);
-    case VDS_EPI_ACCUM_F32: return launch_gemm<128, A_MN, B_MN, VDS_EPI_ACCUM_F32>(a, s);
-    case VDS_EPI_STORE_F32: return launch_gemm<128, A_MN, B_MN, VDS_EPI_STORE_F32>(a, s);
+    case VDS_EPI_ACCUM_F32:
+      return ((a.M + BM - 1) / BM >= 2 && a.cluster == 2) ? launch_gemm<128, A_MN, B_MN, VDS_EPI_ACCUM_F32, 2>(a, s)
+                                                          : launch_gemm<128, A_MN, B_MN, VDS_EPI_ACCUM_F32, 1>(a, s);
+    case VDS_EPI_STORE_F32: return launch_gemm<128, A_MN, B_MN, VDS_EPI_STORE_F32, 1>(a, s);
     default: break;
   }
   if constexpr (!A_MN) {

@@ -38,7 +38,7 @@ class GemmArgs(ctypes.Structure):
         ("C", vp), ("ldc", i64), ("C2", vp), ("ldc2", i64),
         ("bias", vp), ("aux", vp), ("ldaux", i64),
         ("gate", vp), ("gate_stride", i64), ("rows_per_batch", i32),
-        ("remap_rows", i32), ("remap_stride", i32), ("remap_offset", i32), ("tile_n", i32),
+        ("remap_rows", i32), ("remap_stride", i32), ("remap_offset", i32), ("tile_n", i32), ("cluster", i32),
     ]
 
 

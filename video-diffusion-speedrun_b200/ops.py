@@ -26,7 +26,7 @@ def _chk_bf16(*ts):
 
 
 def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=L.EPI_STORE, out=None, out2=None, bias=None,
-         aux=None, gate=None, rows_per_batch=0, splits=1, remap=None, M=None, N=None, K=None, tile_n=0):
+         aux=None, gate=None, rows_per_batch=0, splits=1, remap=None, M=None, N=None, K=None, tile_n=0, cluster=0):
     """D[M,N] = A * B^T on tcgen05 (see include/vds_b200.h: vds_gemm).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b: [N,K] (b_mn=False) or [K,N] (b_mn=True).
@@ -66,6 +66,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=L.EPI_STORE, out=None, out2=N
         args.gate, args.gate_stride = gate.data_ptr(), gate.stride(0)
     args.rows_per_batch = rows_per_batch
     args.tile_n = tile_n
+    args.cluster = cluster
     if remap is not None:
         args.remap_rows, args.remap_stride, args.remap_offset = remap
     L.check(L.lib().vds_gemm(ctypes.byref(args), _stream()), "vds_gemm")
