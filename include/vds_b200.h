@@ -74,7 +74,8 @@ typedef struct vds_gemm_args {
    * tokens (model.py:362) without a concat copy. */
   int32_t remap_rows, remap_stride, remap_offset;
   int32_t tile_n; /* 0 = automatic (128 or 256), 128 = force 128-wide tiles (tuning / tests) */
-  int32_t cluster; /* 2 = 2-CTA clusters with the B tile multicast to both CTAs (opt-in; no gain measured on B200) */
+  int32_t cluster; /* 0 = automatic (2-CTA cta_group::2 256x256 tiles when N % 256 == 0 and the grid fills the chip),
+                      1 = 1-CTA tiles only, 2 = 1-CTA MMAs in 2-CTA clusters with multicast B (experiment) */
 } vds_gemm_args;
 
 int vds_gemm(const vds_gemm_args* args, void* stream);

@@ -125,7 +125,7 @@ def test_gemm_wide_tiles_epilogues(cuda_dev, tile_n):
     _close(dh, hh.grad)
 
 
-@pytest.mark.parametrize("cluster", [0, 2])
+@pytest.mark.parametrize("cluster", [0, 1, 2])
 @pytest.mark.parametrize("M,N,K", [(304, 256, 512), (16416, 1536, 512), (1296, 512, 2048)])
 def test_gemm_cluster_multicast_matches(cuda_dev, M, N, K, cluster):
     """2-CTA clusters with multicast B (auto) vs plain launch; odd numbers of m-tiles leave one CTA of a pair idle."""

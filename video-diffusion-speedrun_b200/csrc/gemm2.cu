@@ -1,0 +1,334 @@
+// 2-CTA tcgen05 GEMM (cta_group::2): a pair of CTAs on one TPC computes a 256 x 256 output tile.
+//
+// Each CTA keeps its own 128 x 64 A tile and HALF (128 rows) of the 256 x 64 B tile per pipeline stage; the
+// leader CTA issues tcgen05.mma.cta_group::2 (M = 256, N = 256), whose tensor cores read both CTAs' shared
+// memory, and each CTA's TMEM receives its 128 accumulator rows.  Per CTA and k-block that is 32 KiB of
+// operand traffic from L2 for 128 x 256 x 64 MACs — half the B bytes of the 1-CTA kernel, which is what the
+// K <= 2048 GEMMs of this model (L2 -> SM bandwidth bound at 128 x 256 tiles) need.
+//
+//   warp 0  TMA producer (both CTAs; .cta_group::2 loads complete on the LEADER's full barrier)
+//   warp 1  MMA issuer (leader only) + TMEM alloc/dealloc (both)
+//   warps 2..9 epilogue (both CTAs, own 128 rows; shared code with gemm.cu)
+#include <cuda.h>
+
+#include "common.h"
+#include "gemm_epilogue.cuh"
+#include "ptx.cuh"
+
+namespace vds {
+
+constexpr int G2_THREADS = 320;
+constexpr int G2_BN = 256;              // tile N of the CTA pair
+constexpr int G2_A_BYTES = BM * BK * 2;           // 16 KiB
+constexpr int G2_B_BYTES = (G2_BN / 2) * BK * 2;  // 16 KiB: this CTA's half of B
+constexpr int G2_STAGE = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_STAGES = 6;
+constexpr int G2_STG = 8 * 4096;
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE + G2_STG + 256 + 1024;
+// shared::cluster address of the same smem offset in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* tmap, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
+  const uint32_t bar_base = smem_base + G2_STAGES * G2_STAGE;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (G2_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * G2_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * G2_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * G2_STAGES + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + G2_STAGES * G2_STAGE + 8 * (2 * G2_STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(full_bar(s), 2);    // one producer arrival per CTA (+ the bytes of both CTAs' loads); leader's is used
+      mbar_init(empty_bar(s), 1);   // leader's MMA commit, multicast to both CTAs
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);   // leader's MMA commit, multicast
+      mbar_init(tempty_bar(a), 16); // 8 epilogue warps x 2 CTAs arrive on the LEADER's barrier
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
+  const int n_tiles = p.N / G2_BN;
+  const int k_iters = (p.K + BK - 1) / BK;
+  const int total_tiles = m_pairs * n_tiles * p.splits;
+  const int tile0 = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const int mt = (tile % m_pairs) * 2 + crank;
+        const int rest = tile / m_pairs;
+        const int nt = rest % n_tiles;
+        const int sp = rest / n_tiles;
+        const int kb0 = sp * p.k_per_split;
+        const int kb1 = min(k_iters, kb0 + p.k_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t lbar = mapa_rank(full_bar(stage), 0);   // leader's full barrier (shared::cluster address)
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * G2_STAGE);
+          else mbar_arrive_cluster(lbar);
+          const uint32_t a_dst = smem_base + stage * G2_STAGE;
+          const uint32_t b_dst = a_dst + G2_A_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d_2sm(a_dst, &tmA, lbar, kb * BK, mt * BM);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              tma_load_2d_2sm(a_dst + i * (BK * 128), &tmA, lbar, mt * BM + i * 64, kb * BK);
+          }
+          const int n0 = nt * G2_BN + crank * (G2_BN / 2);      // this CTA's half of the B tile
+          if constexpr (!B_MN) {
+            tma_load_2d_2sm(b_dst, &tmB, lbar, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < G2_BN / 128; ++i)
+              tma_load_2d_2sm(b_dst + i * (BK * 128), &tmB, lbar, n0 + i * 64, kb * BK);
+          }
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, G2_BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+        const int rest = tile / m_pairs;
+        const int sp = rest / n_tiles;
+        const int kb0 = sp * p.k_per_split;
+        const int kb1 = min(k_iters, kb0 + p.k_per_split);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * G2_BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = smem_base + stage * G2_STAGE;
+            const uint32_t b_addr = a_addr + G2_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t adesc = A_MN ? umma_smem_desc(a_addr + k * 2048, BK * 128, 1024)
+                                          : umma_smem_desc(a_addr + k * 32, 16, 1024);
+              const uint64_t bdesc = B_MN ? umma_smem_desc(b_addr + k * 2048, BK * 128, 1024)
+                                          : umma_smem_desc(b_addr + k * 32, 16, 1024);
+              umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm(empty_bar(stage), 3);                       // slot free in both CTAs
+            if (kb == kb1 - 1) umma_commit_2sm(tfull_bar(acc), 3);      // accumulators complete in both CTAs
+          }
+          __syncwarp();
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const uint32_t leader_tempty0 = mapa_rank(tempty_bar(0), 0);
+    int it = 0;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+      const int mt = (tile % m_pairs) * 2 + crank;
+      const int nt = (tile / m_pairs) % n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = mt * BM + q * 32 + lane;
+      const uint32_t t_base = tmem_base + acc * G2_BN + (static_cast<uint32_t>(q * 32) << 16);
+      constexpr bool kF32 = (EPI == VDS_EPI_ACCUM_F32 || EPI == VDS_EPI_STORE_F32);
+      if constexpr (kF32) {
+#pragma unroll 1
+        for (int c = chalf * (G2_BN / 64); c < (chalf + 1) * (G2_BN / 64); ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_base + c * 32, v);
+          tmem_ld_wait();
+          epilogue_row<EPI>(p, row, nt * G2_BN + c * 32, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
+      } else {
+        uint8_t* stg = smem_gen + G2_STAGES * G2_STAGE + 256 + (warp - 2) * 4096;
+        constexpr int GROUPS = G2_BN / 128;
+#pragma unroll 1
+        for (int gi = 0; gi < GROUPS; ++gi) {
+          const int cg = chalf * GROUPS + gi;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_base + cg * 64, r0);
+          tmem_ld32(t_base + cg * 64 + 32, r1);
+          tmem_ld_wait();
+          if (gi == GROUPS - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
+          }
+          epilogue_group64<EPI>(p, stg, mt * BM + q * 32, nt * G2_BN + cg * 64, r0, r1, lane);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    if (!A_MN) { dims[0] = a.K; dims[1] = a.M; box[0] = BK; box[1] = BM; }
+    else       { dims[0] = a.M; dims[1] = a.K; box[0] = 64; box[1] = BK; }
+    strides[0] = (uint64_t)a.lda * 2;
+    int r = encode_tmap_bf16(&tmA, a.A, 2, dims, strides, box);
+    if (r) return r;
+    if (!B_MN) { dims[0] = a.K; dims[1] = a.N; box[0] = BK; box[1] = G2_BN / 2; }
+    else       { dims[0] = a.N; dims[1] = a.K; box[0] = 64; box[1] = BK; }
+    strides[0] = (uint64_t)a.ldb * 2;
+    r = encode_tmap_bf16(&tmB, a.B, 2, dims, strides, box);
+    if (r) return r;
+  }
+  GemmDev p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  const int k_iters = (a.K + BK - 1) / BK;
+  int splits = (EPI == VDS_EPI_ACCUM_F32) ? (a.splits < 1 ? 1 : a.splits) : 1;
+  if (splits > k_iters) splits = k_iters;
+  p.k_per_split = (k_iters + splits - 1) / splits;
+  p.splits = (k_iters + p.k_per_split - 1) / p.k_per_split;
+  p.C = a.C; p.ldc = a.ldc; p.C2 = a.C2; p.ldc2 = a.ldc2;
+  p.bias = reinterpret_cast<const bf16*>(a.bias);
+  p.aux = reinterpret_cast<const bf16*>(a.aux); p.ldaux = a.ldaux;
+  p.gate = reinterpret_cast<const bf16*>(a.gate); p.gate_stride = a.gate_stride;
+  p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
+  p.remap_rows = a.remap_rows; p.remap_stride = a.remap_stride; p.remap_offset = a.remap_offset;
+
+  auto kern = gemm2_kernel<A_MN, B_MN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM);
+    if (e != cudaSuccess) {
+      set_error("gemm2: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return VDS_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const long long total = (long long)((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / G2_BN) * p.splits;
+  const int max_pairs = num_sms() / 2;
+  const int grid = (int)(total < max_pairs ? total : max_pairs) * 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(G2_THREADS);
+  cfg.dynamicSmemBytes = G2_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  if (e != cudaSuccess) {
+    set_error("gemm2: cluster launch failed: %s", cudaGetErrorString(e));
+    return VDS_ERR_CUDA;
+  }
+  VDS_CHECK_LAUNCH("gemm2");
+  return VDS_OK;
+}
+
+// Entry used by gemm.cu's dispatcher: returns VDS_ERR_UNSUPPORTED when the shape / epilogue has no 2-CTA variant.
+int gemm2_dispatch(const vds_gemm_args& a, cudaStream_t s) {
+  if (a.N % G2_BN != 0) return VDS_ERR_UNSUPPORTED;
+  if (!a.a_mn && !a.b_mn) {
+    switch (a.epilogue) {
+      case VDS_EPI_STORE: return launch_gemm2<false, false, VDS_EPI_STORE>(a, s);
+      case VDS_EPI_BIAS_GELU: return launch_gemm2<false, false, VDS_EPI_BIAS_GELU>(a, s);
+      case VDS_EPI_GATE_RES: return launch_gemm2<false, false, VDS_EPI_GATE_RES>(a, s);
+      default: return VDS_ERR_UNSUPPORTED;
+    }
+  }
+  if (!a.a_mn && a.b_mn) {
+    switch (a.epilogue) {
+      case VDS_EPI_STORE: return launch_gemm2<false, true, VDS_EPI_STORE>(a, s);
+      case VDS_EPI_DGELU: return launch_gemm2<false, true, VDS_EPI_DGELU>(a, s);
+      default: return VDS_ERR_UNSUPPORTED;
+    }
+  }
+  if (a.a_mn && a.b_mn && a.epilogue == VDS_EPI_ACCUM_F32) return launch_gemm2<true, true, VDS_EPI_ACCUM_F32>(a, s);
+  return VDS_ERR_UNSUPPORTED;
+}
+
+}  // namespace vds

@@ -1,0 +1,262 @@
+// Shared by gemm.cu (1-CTA tiles) and gemm2.cu (2-CTA cta_group::2 tiles): device-side argument block and the
+// fused epilogues (thread == accumulator row, coalesced through a per-warp swizzled smem transpose).
+#pragma once
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vds {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+
+struct GemmDev {
+  int M, N, K;
+  int splits, k_per_split;
+  void* C;
+  long long ldc;
+  void* C2;
+  long long ldc2;
+  const bf16* bias;
+  const bf16* aux;
+  long long ldaux;
+  const bf16* gate;
+  long long gate_stride;
+  int rows_per_batch;
+  int remap_rows, remap_stride, remap_offset;
+};
+
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 rounding of the outputs): the libm
+// erff costs ~4x more instructions and made the GELU epilogues, not the MMAs, the bottleneck of the MLP GEMMs.
+// Returns erf(x/sqrt2) and exp(-x^2/2) (shared by GELU and its derivative).
+__device__ __forceinline__ float erf_as(float x, float& gauss) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  gauss = exp2f(-0.72134752044448170368f * x * x);   // exp(-x^2/2) = exp(-z^2)
+  const float e = fmaf(-poly * t, gauss, 1.0f);
+  return copysignf(e, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float g;
+  return 0.5f * x * (1.0f + erf_as(x, g));
+}
+__device__ __forceinline__ float dgelu_erf(float x) {
+  float g;
+  const float cdf = 0.5f * (1.0f + erf_as(x, g));
+  return fmaf(x * 0.39894228040143267794f, g, cdf);
+}
+
+__device__ __forceinline__ void ld8_bf16(const bf16* p, float (&o)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+}
+__device__ __forceinline__ void st8_bf16(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// ---- coalesced bf16 epilogue -------------------------------------------------------------------------------
+// TMEM hands each thread one output ROW; storing rows straight from registers makes every warp store touch 32
+// different lines (32 partial-sector transactions), which caps the K = 512 GEMMs well below the MMA rate.  Each
+// epilogue warp therefore transposes 32 rows x 64 columns through a private 4 KiB shared-memory buffer
+// (16-byte chunks XOR-swizzled by row) so that one warp instruction moves 4 full 128-byte row segments.
+__device__ __forceinline__ uint32_t stg_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+struct RowMap {   // global row of local row rr (0..31) for loads / stores, -1 if out of range
+  int row0, M, remap_rows, remap_stride, remap_offset;
+  __device__ __forceinline__ long long out_row(int rr) const {
+    const int r = row0 + rr;
+    if (r >= M) return -1;
+    if (remap_rows > 0) return (long long)(r / remap_rows) * remap_stride + remap_offset + r % remap_rows;
+    return r;
+  }
+  __device__ __forceinline__ long long in_row(int rr) const { return row0 + rr < M ? row0 + rr : -1; }
+};
+
+// staging -> global: 8 instructions, lane = (row within group of 4, 16-byte chunk)
+__device__ __forceinline__ void stg_store(const uint8_t* stg, bf16* C, long long ldc, const RowMap& rm, int col0,
+                                          int N, int lane, bool remap) {
+  const int ch = lane & 7, col = col0 + ch * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int rr = k * 4 + (lane >> 3);
+    const long long row = remap ? rm.out_row(rr) : rm.in_row(rr);
+    const uint4 v = *reinterpret_cast<const uint4*>(stg + stg_off(rr, ch));
+    if (row >= 0 && col < N) *reinterpret_cast<uint4*>(C + row * ldc + col) = v;
+  }
+}
+// global -> staging
+__device__ __forceinline__ void stg_load(uint8_t* stg, const bf16* A, long long lda, const RowMap& rm, int col0, int N,
+                                         int lane) {
+  const int ch = lane & 7, col = col0 + ch * 8;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int rr = k * 4 + (lane >> 3);
+    const long long row = rm.in_row(rr);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row >= 0 && col < N) v = *reinterpret_cast<const uint4*>(A + row * lda + col);
+    *reinterpret_cast<uint4*>(stg + stg_off(rr, ch)) = v;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack8(uint4 u, float (&o)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+}
+
+// One warp, 32 rows x 64 columns [col0, col0 + 64): acc = 64 fp32 per thread (its own row).
+template <int EPI>
+__device__ __forceinline__ void epilogue_group64(const GemmDev& p, uint8_t* stg, int row0, int col0,
+                                                 const uint32_t (&r0)[32], const uint32_t (&r1)[32], int lane) {
+  RowMap rm{row0, p.M, p.remap_rows, p.remap_stride, p.remap_offset};
+  const int my_row = row0 + lane;
+  if constexpr (EPI == VDS_EPI_GATE_RES || EPI == VDS_EPI_DGELU) {
+    stg_load(stg, p.aux, p.ldaux, rm, col0, p.N, lane);
+    __syncwarp();
+  }
+  uint4 keep[8];  // first output (bf16 Linear result) kept packed while the second goes through the buffer
+  const int b = (EPI == VDS_EPI_GATE_RES) ? min(my_row, p.M - 1) / p.rows_per_batch : 0;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const int col = col0 + g * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]);
+    const bool col_ok = col < p.N;
+    if constexpr (EPI != VDS_EPI_DGELU) {
+      if (p.bias != nullptr && col_ok) {
+        float bb[8];
+        ld8_bf16(p.bias + col, bb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += bb[j];
+      }
+    }
+    uint8_t* slot = stg + stg_off(lane, g);
+    if constexpr (EPI == VDS_EPI_STORE) {
+      *reinterpret_cast<uint4*>(slot) = pack8(acc);
+    } else if constexpr (EPI == VDS_EPI_BIAS_GELU) {
+      float act[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = bf16_round(acc[j]);
+        act[j] = gelu_erf(acc[j]);
+      }
+      keep[g] = pack8(acc);
+      *reinterpret_cast<uint4*>(slot) = pack8(act);
+    } else if constexpr (EPI == VDS_EPI_GATE_RES) {
+      float g8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, x8[8], o8[8];
+      if (col_ok) ld8_bf16(p.gate + (long long)b * p.gate_stride + col, g8);
+      unpack8(*reinterpret_cast<const uint4*>(slot), x8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = bf16_round(acc[j]);                      // Linear output is bf16 in the reference
+        o8[j] = x8[j] + bf16_round(acc[j] * g8[j]);      // x + (out * gate), each op rounded to bf16
+      }
+      keep[g] = pack8(acc);
+      *reinterpret_cast<uint4*>(slot) = pack8(o8);
+    } else if constexpr (EPI == VDS_EPI_DGELU) {
+      float h8[8];
+      unpack8(*reinterpret_cast<const uint4*>(slot), h8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= dgelu_erf(h8[j]);
+      *reinterpret_cast<uint4*>(slot) = pack8(acc);
+    }
+  }
+  __syncwarp();
+  if constexpr (EPI == VDS_EPI_STORE || EPI == VDS_EPI_DGELU) {
+    stg_store(stg, reinterpret_cast<bf16*>(p.C), p.ldc, rm, col0, p.N, lane, EPI == VDS_EPI_STORE);
+  } else {
+    stg_store(stg, reinterpret_cast<bf16*>(p.C2), p.ldc2, rm, col0, p.N, lane, false);
+    if (p.C != nullptr) {
+      __syncwarp();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(stg + stg_off(lane, g)) = keep[g];
+      __syncwarp();
+      stg_store(stg, reinterpret_cast<bf16*>(p.C), p.ldc, rm, col0, p.N, lane, false);
+    }
+  }
+  __syncwarp();
+}
+
+// One thread handles 32 consecutive columns [col0, col0+32) of output row `row`.
+template <int EPI>
+__device__ __forceinline__ void epilogue_row(const GemmDev& p, int row, int col0, const uint32_t (&raw)[32]) {
+  if (row >= p.M) return;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int col = col0 + g * 8;
+    if (col >= p.N) break;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(raw[g * 8 + j]);
+
+    if constexpr (EPI == VDS_EPI_ACCUM_F32) {
+      float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
+      red_add_v4(c, acc[0], acc[1], acc[2], acc[3]);
+      red_add_v4(c + 4, acc[4], acc[5], acc[6], acc[7]);
+    } else {
+      if constexpr (EPI != VDS_EPI_DGELU) {
+        if (p.bias != nullptr) {
+          float b[8];
+          ld8_bf16(p.bias + col, b);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += b[j];
+        }
+      }
+      if constexpr (EPI == VDS_EPI_STORE_F32) {
+        float* c = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
+        *reinterpret_cast<float4*>(c) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(c + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      } else if constexpr (EPI == VDS_EPI_STORE) {
+        long long orow = row;
+        if (p.remap_rows > 0)
+          orow = (long long)(row / p.remap_rows) * p.remap_stride + p.remap_offset + row % p.remap_rows;
+        st8_bf16(reinterpret_cast<bf16*>(p.C) + orow * p.ldc + col, acc);
+      } else if constexpr (EPI == VDS_EPI_BIAS_GELU) {
+        float act[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] = bf16_round(acc[j]);
+          act[j] = gelu_erf(acc[j]);
+        }
+        if (p.C != nullptr) st8_bf16(reinterpret_cast<bf16*>(p.C) + (long long)row * p.ldc + col, acc);
+        st8_bf16(reinterpret_cast<bf16*>(p.C2) + (long long)row * p.ldc2 + col, act);
+      } else if constexpr (EPI == VDS_EPI_GATE_RES) {
+        const int b = row / p.rows_per_batch;
+        float g8[8], x8[8], o8[8];
+        ld8_bf16(p.gate + (long long)b * p.gate_stride + col, g8);
+        ld8_bf16(p.aux + (long long)row * p.ldaux + col, x8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] = bf16_round(acc[j]);                      // Linear output is bf16 in the reference
+          o8[j] = x8[j] + bf16_round(acc[j] * g8[j]);      // x + (out * gate), each op rounded to bf16
+        }
+        if (p.C != nullptr) st8_bf16(reinterpret_cast<bf16*>(p.C) + (long long)row * p.ldc + col, acc);
+        st8_bf16(reinterpret_cast<bf16*>(p.C2) + (long long)row * p.ldc2 + col, o8);
+      } else if constexpr (EPI == VDS_EPI_DGELU) {
+        float h8[8];
+        ld8_bf16(p.aux + (long long)row * p.ldaux + col, h8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= dgelu_erf(h8[j]);
+        st8_bf16(reinterpret_cast<bf16*>(p.C) + (long long)row * p.ldc + col, acc);
+      }
+    }
+  }
+}
+
+
+}  // namespace vds
