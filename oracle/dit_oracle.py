@@ -291,3 +291,26 @@ def make_inputs(cfg, B, thw_latent, Lc, Dc, seed):
     context = torch.randn((B, Lc, Dc), generator=g).bfloat16()
     t = shift_time(torch.sigmoid(torch.randn((B,), generator=g).bfloat16()))
     return latent, noise, context, t
+
+
+def sample_loop(P, cfg, prompt_embeds, latents, inference_steps, cfg_scale=6.0, table_dtype=torch.bfloat16,
+                model_dtype=torch.bfloat16):
+    """sampling/sample.py:107-146 restated: shifted-time Euler, CFG with zero negative embeds, fp32 accumulator.
+    `P` / inputs are used in `model_dtype` like the reference's ``model.to(device, bf16)`` (sample.py:63)."""
+    Pm = {k: v.to(model_dtype) for k, v in P.items()}
+    prompt_embeds = prompt_embeds.to(model_dtype)
+    negative = torch.zeros_like(prompt_embeds)
+    latents = latents.to(model_dtype)
+    acc = latents.to(torch.float32)
+    for i in range(inference_steps, 0, -1):
+        t = shift_time(i / inference_steps)
+        t_next = shift_time((i - 1) / inference_steps)
+        dt = t - t_next
+        tt = torch.tensor([t] * latents.shape[0]).to(latents.device, model_dtype)
+        out = dit_forward(Pm, cfg, latents, prompt_embeds, tt, table_dtype=table_dtype)
+        if cfg_scale > 1:
+            un = dit_forward(Pm, cfg, latents, negative, tt, table_dtype=table_dtype)
+            out = un + cfg_scale * (out - un)
+        acc = acc + dt * out.to(torch.float32)
+        latents = acc.to(model_dtype)
+    return acc
