@@ -427,14 +427,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         if (elect_one()) {
           const uint32_t q = sQ + st * 2 * QT_BYTES, d_o = q + QT_BYTES;
+          const uint32_t tPT = tmem + 256 + bb * 128, tDSTm = tPT + 64;   // bf16 P^T / dS^T in the retired S^T / dP^T columns
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // dV += P^T dO : A = P^T [128 x 64] K-major, B = dO MN-major (N = d)
-            umma_bf16(tDV, umma_smem_desc(sPT + kk * 32, 16, 1024), umma_smem_desc(d_o + kk * 2048, QT_HALF, 1024),
-                      idesc_acc, (i > 0 || kk > 0));
+          for (int kk = 0; kk < 4; ++kk)   // dV += P^T dO : A = P^T (TMEM, 8 columns per k-step), B = dO MN-major (N = d)
+            umma_bf16_ts(tDV, tPT + kk * 8, umma_smem_desc(d_o + kk * 2048, QT_HALF, 1024), idesc_acc,
+                         (i > 0 || kk > 0));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)   // dK += dS^T Q
-            umma_bf16(tDK, umma_smem_desc(sDST + kk * 32, 16, 1024), umma_smem_desc(q + kk * 2048, QT_HALF, 1024),
-                      idesc_acc, (i > 0 || kk > 0));
+          for (int kk = 0; kk < 4; ++kk)   // dK += dS^T Q : A = dS^T (TMEM)
+            umma_bf16_ts(tDK, tDSTm + kk * 8, umma_smem_desc(q + kk * 2048, QT_HALF, 1024), idesc_acc,
+                         (i > 0 || kk > 0));
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)   // dQ^T = K^T dS^T : A = K MN-major (M = d), B = dS^T MN-major (N = q)
             umma_bf16(tmem + 256 + bb * 128, desc_mnmajor(sK, kk), umma_smem_desc(sDST + kk * 2048, 16, 1024),
@@ -515,13 +516,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           }
         }
-        if (i > 0) mbar_wait(mma_done + 8 * (bb ^ 1), ((i - 1) >> 1) & 1);   // P^T / dS^T smem consumed
+        // P^T and dS^T become TMEM-resident A operands (they overwrite the S^T / dP^T columns this thread just
+        // read); dS^T additionally goes to shared memory as the B operand of dQ^T = K^T dS^T.
+        tmem_st32(tST, pp);
+        tmem_st32(tDPT, dd);
+        if (i > 0) mbar_wait(mma_done + 8 * (bb ^ 1), ((i - 1) >> 1) & 1);   // dS^T smem tile consumed by dQ^T(i-1)
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint32_t off = sw128_offset(r, g);
-          *reinterpret_cast<uint4*>(gPT + off) = make_uint4(pp[g * 4], pp[g * 4 + 1], pp[g * 4 + 2], pp[g * 4 + 3]);
-          *reinterpret_cast<uint4*>(gDST + off) = make_uint4(dd[g * 4], dd[g * 4 + 1], dd[g * 4 + 2], dd[g * 4 + 3]);
-        }
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<uint4*>(gDST + sw128_offset(r, g)) =
+              make_uint4(dd[g * 4], dd[g * 4 + 1], dd[g * 4 + 2], dd[g * 4 + 3]);
+        tmem_st_wait();
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(pds_full);

@@ -153,49 +153,85 @@ struct NormArgs {
 
 template <int NV>
 __global__ void __launch_bounds__(256) rmsnorm_mod_fwd_kernel(const NormArgs a) {
+  // Each warp owns RPW consecutive rows: all their 16-byte groups (and the per-sample scale / shift / weight
+  // groups) are requested up front, so one DRAM round trip covers RPW rows instead of one.
+  constexpr int RPW = (NV <= 3) ? 4 : 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
-  if (row >= a.rows_out) return;
-  const int b = row / a.rows_per_batch_out, r = row % a.rows_per_batch_out;
-  const long long in_row = (long long)b * a.in_batch_stride + a.in_row_offset + r;
-  const bf16* xr = a.x + in_row * a.h;
+  const int row0 = (blockIdx.x * 8 + warp) * RPW;
+  if (row0 >= a.rows_out) return;
   const int ng = a.h / 8;
-  float v[NV][8];
-  float ss = 0.f;
+  uint4 raw[RPW][NV];
+  int bidx[RPW];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    if (i * 32 + lane < ng) {
-      ld8(xr + (i * 32 + lane) * 8, v[i]);
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int row = min(row0 + rr, a.rows_out - 1);
+    const int b = row / a.rows_per_batch_out, r = row % a.rows_per_batch_out;
+    bidx[rr] = b;
+    const bf16* xr = a.x + ((long long)b * a.in_batch_stride + a.in_row_offset + r) * a.h;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
-    }
+    for (int i = 0; i < NV; ++i)
+      if (i * 32 + lane < ng) raw[rr][i] = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
   }
-  ss = warp_sum(ss);
-  const float rstd = rsqrtf(ss / (float)a.h + a.eps);
-  if (lane == 0 && a.rstd != nullptr) a.rstd[row] = rstd;
-  bf16* yr = a.y + (long long)row * a.h;
+  // modulation of the first row's sample (rows of one warp straddle samples at most once; handled below)
+  uint4 rsc[NV], rsh[NV], rw[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     if (i * 32 + lane < ng) {
       const int c = (i * 32 + lane) * 8;
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = v[i][j] * rstd;
-      if (a.weight != nullptr) {
-        float w[8];
-        ld8(a.weight + c, w);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] *= w[j];
-      }
       if (a.scale != nullptr) {
-        float sc[8], sh[8];
-        ld8(a.scale + (long long)b * a.mod_stride + c, sc);
-        ld8(a.shift + (long long)b * a.mod_stride + c, sh);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = bf16_round(bf16_round(o[j]) * bf16_round(1.0f + sc[j])) + sh[j];
+        rsc[i] = *reinterpret_cast<const uint4*>(a.scale + (long long)bidx[0] * a.mod_stride + c);
+        rsh[i] = *reinterpret_cast<const uint4*>(a.shift + (long long)bidx[0] * a.mod_stride + c);
       }
-      st8(yr + c, o);
+      if (a.weight != nullptr) rw[i] = *reinterpret_cast<const uint4*>(a.weight + c);
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int row = row0 + rr;
+    if (row >= a.rows_out) break;
+    float v[NV][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i * 32 + lane < ng) {
+        unpack8f(raw[rr][i], v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += v[i][j] * v[i][j];
+      }
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / (float)a.h + a.eps);
+    if (lane == 0 && a.rstd != nullptr) a.rstd[row] = rstd;
+    bf16* yr = a.y + (long long)row * a.h;
+    const bool same = bidx[rr] == bidx[0];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (i * 32 + lane < ng) {
+        const int c = (i * 32 + lane) * 8;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = v[i][j] * rstd;
+        if (a.weight != nullptr) {
+          float w[8];
+          unpack8f(rw[i], w);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] *= w[j];
+        }
+        if (a.scale != nullptr) {
+          float sc[8], sh[8];
+          if (same) {
+            unpack8f(rsc[i], sc);
+            unpack8f(rsh[i], sh);
+          } else {
+            ld8(a.scale + (long long)bidx[rr] * a.mod_stride + c, sc);
+            ld8(a.shift + (long long)bidx[rr] * a.mod_stride + c, sh);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = bf16_round(bf16_round(o[j]) * bf16_round(1.0f + sc[j])) + sh[j];
+        }
+        st8(yr + c, o);
+      }
     }
   }
 }
@@ -703,7 +739,7 @@ int vds_rmsnorm_mod_fwd(const void* x, void* y, float* rstd, const void* weight,
   a.rows_out = B * rows_per_batch_out; a.h = h; a.rows_per_batch_out = rows_per_batch_out;
   a.in_batch_stride = in_batch_stride; a.in_row_offset = in_row_offset; a.eps = eps;
   const int nvn = (h + 255) / 256;
-#define VDS_L(NVV) rmsnorm_mod_fwd_kernel<NVV><<<ceil_div(a.rows_out, 8), 256, 0, (cudaStream_t)stream>>>(a)
+#define VDS_L(NVV) rmsnorm_mod_fwd_kernel<NVV><<<ceil_div(a.rows_out, 8 * ((NVV) <= 3 ? 4 : 2)), 256, 0, (cudaStream_t)stream>>>(a)
   if (nvn <= 2) VDS_L(2); else if (nvn <= 3) VDS_L(3); else if (nvn <= 5) VDS_L(5); else VDS_L(8);
 #undef VDS_L
   VDS_CHECK_LAUNCH("rmsnorm_mod_fwd");
