@@ -140,6 +140,9 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
                  int64_t ldkv_acc, int q_splits, int B, int nh, int Lq, int Lk, int head_dim, float scale,
                  void* stream);
 
+/* tuning aid: per-iteration clock64 trace of one CTA of attn_bwd (NULL disables). */
+int vds_debug_attn_bwd_trace(void* buf);
+
 /* ------------------------------------------------------------------------------------------ loss / optimizer
  * loss_sum += mean_b mean_rest (bf16(x-noise) - out)^2 ; d_out = 2(out - v)/(B*per) * grad_scale
  * (* grad_scale_dev[0] if non-NULL: the upstream autograd scalar, read on the device).  train.py:117-125 */

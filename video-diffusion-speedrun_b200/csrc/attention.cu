@@ -293,6 +293,27 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __r
   }
 }
 
+// K-major operand WITHOUT swizzle, 16 columns wide (one k-step): 8-row x 16-byte core matrices, the two 8-column
+// halves 128 B apart (LBO), consecutive 8-row groups 256 B apart (SBO).
+__device__ __forceinline__ uint64_t desc_k16_noswz(uint32_t addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(128 >> 4) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+__device__ __forceinline__ uint32_t k16_off(int row) { return (row >> 3) * 256 + (row & 7) * 16; }
+// x = hi + mid + lo with three bf16 terms (fp32-exact to ~2^-24 relative): the per-query statistics ride through
+// the tensor core as an extra rank-3 update instead of being re-read from shared memory for every element.
+__device__ __forceinline__ uint4 split3_bf16(float x) {
+  if (!(fabsf(x) < 3.0e38f)) return make_uint4(pack_bf16x2(x, 0.f), 0u, 0u, 0u);   // +-inf (masked query rows)
+  const float hi = bf16_round(x);
+  const float mid = bf16_round(x - hi);
+  const float lo = bf16_round(x - hi - mid);
+  return make_uint4(pack_bf16x2(hi, mid), pack_bf16x2(lo, 0.f), 0u, 0u);
+}
+
 struct AttnBwdParams {
   const float* lse; const float* delta;   // [B, nh, Lq]
   float* dq_acc; long long lddq;           // fp32 [B, Lq, lddq] (+=)
@@ -301,7 +322,13 @@ struct AttnBwdParams {
   float* dk_acc; float* dv_acc; long long ldkv_acc;  // fp32 accumulation targets when q_splits > 1
   int Lq, Lk, nh, q_splits;
   float scale_log2, scale;
+  long long* dbg;   // optional per-iteration clock64 trace of CTA (0,0,0): [iter][8] (debug / tuning only)
 };
+#define VDS_TRACE(slot, it)                                                                      \
+  do {                                                                                           \
+    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (it) < 160) \
+      p.dbg[(it) * 8 + (slot)] = clock64();                                                      \
+  } while (0)
 
 // Backward v1.  CTA = one 128-row K/V tile of one (b, head), looping over 64-row query sub-tiles:
 //   S^T = K Q^T, dP^T = V dO^T          (TMEM, double-buffered)        M=128 (kv) N=64 (q)  K=128 (d)
@@ -340,7 +367,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* s_stat = reinterpret_cast<float*>(gen + BWD_OFF_STAT);   // [buf][lse|delta][64]
   const uint32_t bars = base + BWD_OFF_BAR;
   const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 32, sdp_full = bars + 56,
-                 pds_full = bars + 72, mma_done = bars + 80, dq_drained = bars + 96, tmem_slot = bars + 112;
+                 pds_full = bars + 72, mma_done = bars + 80, dq_drained = bars + 96, tmem_slot = bars + 112,
+                 stat_full = bars + 120;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + BWD_OFF_BAR + 112);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -359,6 +387,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(sdp_full + 8 * s, 1);
       mbar_init(mma_done + 8 * s, 1);
       mbar_init(dq_drained + 8 * s, 128);
+      mbar_init(stat_full + 8 * s, 128);
     }
     mbar_init(pds_full, 128);
     fence_mbar_init();
@@ -402,18 +431,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int bb = k & 1, st = k % 3;
         mbar_wait(qdo_full + 8 * st, (k / 3) & 1);
         if (k >= 2) mbar_wait(dq_drained + 8 * bb, ((k >> 1) - 1) & 1);
+        mbar_wait(stat_full + 8 * bb, (k >> 1) & 1);
         tc_fence_after();
         if (elect_one()) {
+          VDS_TRACE(0, k);   // S/dP(k) issue
           const uint32_t q = sQ + st * 2 * QT_BYTES, d_o = q + QT_BYTES;
           const uint32_t tST = tmem + 256 + bb * 128, tDPT = tST + 64;
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)   // S^T = K Q^T : B = Q tile, K-major, 64 rows per half
             umma_bf16(tST, desc_kmajor(sK, kk), umma_smem_desc(q + (kk >> 2) * QT_HALF + (kk & 3) * 32, 16, 1024),
                       idesc_s, kk > 0);
+          umma_bf16(tST, desc_k16_noswz(sPT), desc_k16_noswz(sPT + 4096 + (bb * 2 + 0) * 2048), idesc_s, 1);  // - lse
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)   // dP^T = V dO^T
             umma_bf16(tDPT, desc_kmajor(sV, kk), umma_smem_desc(d_o + (kk >> 2) * QT_HALF + (kk & 3) * 32, 16, 1024),
                       idesc_s, kk > 0);
+          umma_bf16(tDPT, desc_k16_noswz(sPT), desc_k16_noswz(sPT + 4096 + (bb * 2 + 1) * 2048), idesc_s, 1);  // - delta
           umma_commit(sdp_full + 8 * bb);
         }
         __syncwarp();
@@ -426,6 +459,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(pds_full, i & 1);
         tc_fence_after();
         if (elect_one()) {
+          VDS_TRACE(1, i);   // dV/dK/dQ(i) issue
           const uint32_t q = sQ + st * 2 * QT_BYTES, d_o = q + QT_BYTES;
           const uint32_t tPT = tmem + 256 + bb * 128, tDSTm = tPT + 64;   // bf16 P^T / dS^T in the retired S^T / dP^T columns
 #pragma unroll
@@ -455,25 +489,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const long long stat_base = ((long long)b * p.nh + head) * p.Lq;
       const float* stat_src = (ct < 64 ? p.lse : p.delta) + stat_base;
       const int sc = ct & 63;
-      {
-        const int q = qt0 * QSUB + sc;
-        s_stat[(ct < 64 ? 0 : 64) + sc] = q < p.Lq ? stat_src[q] * (ct < 64 ? -1.0f : p.scale) : 0.f;
+      const float inv_sl2 = 1.0f / p.scale_log2;
+      // value this thread contributes to the statistics tile of sub-tile k: -lse/scale_log2 (ct < 64) or -delta
+      auto stat_value = [&](int k) -> float {
+        const int q = (qt0 + k) * QSUB + sc;
+        if (q >= p.Lq) return ct < 64 ? -INFINITY : 0.f;        // padded query row: exp2(-inf) = 0
+        return ct < 64 ? -stat_src[q] * inv_sl2 : -stat_src[q];
+      };
+      auto stat_store = [&](int k, float v) {
+        uint8_t* tile = gPT + 4096 + ((k & 1) * 2 + (ct < 64 ? 0 : 1)) * 2048;
+        *reinterpret_cast<uint4*>(tile + k16_off(sc)) = split3_bf16(v);
+        *reinterpret_cast<uint4*>(tile + k16_off(sc) + 128) = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+        mbar_arrive(stat_full + 8 * (k & 1));
+      };
+      {  // constant A operand of the statistics k-step: ones in columns 0..2 of every kv row
+        const float one = 1.0f;
+        *reinterpret_cast<uint4*>(gPT + k16_off(ct)) = make_uint4(pack_bf16x2(one, one), pack_bf16x2(one, 0.f), 0u, 0u);
+        *reinterpret_cast<uint4*>(gPT + k16_off(ct) + 128) = make_uint4(0u, 0u, 0u, 0u);
       }
+      stat_store(0, stat_value(0));
+      if (n_q > 1) stat_store(1, stat_value(1));
       const bool kv_full_tile = kv0 + 128 <= p.Lk;
       for (int i = 0; i < n_q; ++i) {
         const int bb = i & 1;
-        const int q0 = (qt0 + i) * QSUB;
-        float next_stat = 0.f;
-        if (i + 1 < n_q) {
-          const int q = q0 + QSUB + sc;
-          next_stat = q < p.Lq ? stat_src[q] * (ct < 64 ? -1.0f : p.scale) : 0.f;   // -lse | delta*scale
-        }
-        named_bar_sync(1, 128);            // stats of this sub-tile visible; previous iteration fully done
-        const float* lse_s = s_stat + bb * 128;
-        const float* del_s = lse_s + 64;
+        const float next_stat = (i + 2 < n_q) ? stat_value(i + 2) : 0.f;   // prefetched; stored at the end of this iteration
         mbar_wait(sdp_full + 8 * bb, (i >> 1) & 1);
         tc_fence_after();
-        const int qvalid = p.Lq - q0;
+        if (ct == 0) VDS_TRACE(2, i);   // compute sees S/dP(i)
         const uint32_t tST = tmem + 256 + bb * 128 + lane_off, tDPT = tST + 64;
         uint32_t pp[32], dd[32];
 #pragma unroll
@@ -482,44 +525,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_ld32(tST + c * 32, sv);
           tmem_ld32(tDPT + c * 32, dv);
           tmem_ld_wait();
-          if (kv_full_tile && qvalid >= QSUB) {
+          // S^T already carries -lse (and dP^T carries -delta) from the statistics k-step of the MMA
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 nl = *reinterpret_cast<const float4*>(lse_s + c * 32 + e);
-              const float4 dl = *reinterpret_cast<const float4*>(del_s + c * 32 + e);
-              const float nls[4] = {nl.x, nl.y, nl.z, nl.w}, dls[4] = {dl.x, dl.y, dl.z, dl.w};
-              float pv[4], ds[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                pv[u] = ex2(fmaf(__uint_as_float(sv[e + u]), p.scale_log2, nls[u]));
-                ds[u] = pv[u] * fmaf(__uint_as_float(dv[e + u]), p.scale, -dls[u]);
-              }
-              pp[c * 16 + (e >> 1)] = pack_bf16x2(pv[0], pv[1]);
-              pp[c * 16 + (e >> 1) + 1] = pack_bf16x2(pv[2], pv[3]);
-              dd[c * 16 + (e >> 1)] = pack_bf16x2(ds[0], ds[1]);
-              dd[c * 16 + (e >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = ex2(__uint_as_float(sv[e]) * p.scale_log2);
+            float p1 = ex2(__uint_as_float(sv[e + 1]) * p.scale_log2);
+            if (!kv_full_tile) {
+              p0 = kv_ok ? p0 : 0.f;
+              p1 = kv_ok ? p1 : 0.f;
             }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              float pv[2], ds[2];
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int col = c * 32 + e + u;
-                float pr = ex2(fmaf(__uint_as_float(sv[e + u]), p.scale_log2, lse_s[col]));
-                pr = (kv_ok && col < qvalid) ? pr : 0.f;
-                pv[u] = pr;
-                ds[u] = pr * fmaf(__uint_as_float(dv[e + u]), p.scale, -del_s[col]);
-              }
-              pp[c * 16 + (e >> 1)] = pack_bf16x2(pv[0], pv[1]);
-              dd[c * 16 + (e >> 1)] = pack_bf16x2(ds[0], ds[1]);
-            }
+            const float d0 = p0 * (__uint_as_float(dv[e]) * p.scale);
+            const float d1 = p1 * (__uint_as_float(dv[e + 1]) * p.scale);
+            pp[c * 16 + (e >> 1)] = pack_bf16x2(p0, p1);
+            dd[c * 16 + (e >> 1)] = pack_bf16x2(d0, d1);
           }
         }
         // P^T and dS^T become TMEM-resident A operands (they overwrite the S^T / dP^T columns this thread just
         // read); dS^T additionally goes to shared memory as the B operand of dQ^T = K^T dS^T.
         tmem_st32(tST, pp);
         tmem_st32(tDPT, dd);
+        if (ct == 0) VDS_TRACE(3, i);   // math done
         if (i > 0) mbar_wait(mma_done + 8 * (bb ^ 1), ((i - 1) >> 1) & 1);   // dS^T smem tile consumed by dQ^T(i-1)
 #pragma unroll
         for (int g = 0; g < 8; ++g)
@@ -529,7 +554,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(pds_full);
-        if (i + 1 < n_q) s_stat[(bb ^ 1) * 128 + (ct < 64 ? 0 : 64) + sc] = next_stat;
+        if (ct == 0) VDS_TRACE(4, i);   // pds arrive
+        if (i + 2 < n_q) stat_store(i + 2, next_stat);   // buffer bb: its MMAs (S^T / dP^T of sub-tile i) are complete
       }
     } else if (warp >= 8) {
       // ------------------------------------------------------------ dQ drain warpgroup (thread == d)
@@ -541,12 +567,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int bb = i & 1;
         mbar_wait(mma_done + 8 * bb, (i >> 1) & 1);
         tc_fence_after();
+        if (leader) VDS_TRACE(5, i);   // drain sees dQ(i)
         uint32_t v0[32], v1[32];
         tmem_ld32(tmem + 256 + bb * 128 + lane_off, v0);
         tmem_ld32(tmem + 256 + bb * 128 + lane_off + 32, v1);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(dq_drained + 8 * bb);
+        if (leader) VDS_TRACE(6, i);   // dq_drained arrive
         if (leader) bulk_wait_group_read0();      // previous reduction has finished reading the staging tile
         named_bar_sync(2, 128);
 #pragma unroll
@@ -610,6 +638,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+long long* g_attn_bwd_trace = nullptr;   // set through vds_debug_attn_bwd_trace (tuning only)
+
 static int make_tmap_tokens(CUtensorMap* tm, const void* ptr, long long ld, int L, int nh, int B, int box_rows = 128) {
   uint64_t dims[4] = {(uint64_t)HD, (uint64_t)L, (uint64_t)nh, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)HD * 2, (uint64_t)L * (uint64_t)ld * 2};
@@ -629,6 +659,12 @@ static int make_tmap_dq(CUtensorMap* tm, const float* ptr, long long ld, int L, 
 using namespace vds;
 
 extern "C" {
+
+/* tuning aid: when non-NULL, CTA (0,0,0) of every following attn_bwd launch writes clock64 stamps [iter][8] here */
+int vds_debug_attn_bwd_trace(void* buf) {
+  vds::g_attn_bwd_trace = (long long*)buf;
+  return VDS_OK;
+}
 
 /* q: [B, Lq, ldq] (head h at column h*128), k/v: [B, Lk, ldk|ldv]; out: [B, Lq, ldo]; lse: [B, nh, Lq] fp32 */
 int vds_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
@@ -692,6 +728,7 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   p.dk_acc = dk_acc; p.dv_acc = dv_acc; p.ldkv_acc = ldkv_acc;
   p.Lq = Lq; p.Lk = Lk; p.nh = nh; p.q_splits = q_splits;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.dbg = g_attn_bwd_trace;
   dim3 grid(((Lk + 127) / 128) * q_splits, nh, B);
   attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, tdo, tdq, p);
   VDS_CHECK_LAUNCH("attn_bwd");

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "vds_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, f32, vp],
     "vds_attn_bwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp, i64, vp, vp,
                      i64, i32, i32, i32, i32, i32, i32, f32, vp],
+    "vds_debug_attn_bwd_trace": [vp],
     "vds_loss_fwd_bwd": [vp, vp, vp, vp, vp, vp, i32, i64, f32, vp, vp],
     "vds_adamw": [vp, vp, vp, vp, vp, vp, vp, vp, i32, fp, fp, i32, f32, f32, f32, i32, f32, vp],
 }
