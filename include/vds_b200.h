@@ -142,6 +142,8 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
 
 /* tuning aid: per-iteration clock64 trace of one CTA of attn_bwd (NULL disables). */
 int vds_debug_attn_bwd_trace(void* buf);
+/* tuning aid: CTA 0 of the 2-CTA GEMM writes {total, wait(tmem empty), wait(smem full), tiles, epi wait, epi busy} cycles. */
+int vds_debug_gemm2_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------ loss / optimizer
  * loss_sum += mean_b mean_rest (bf16(x-noise) - out)^2 ; d_out = 2(out - v)/(B*per) * grad_scale

@@ -258,6 +258,7 @@ static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
   p.gate = reinterpret_cast<const bf16*>(a.gate); p.gate_stride = a.gate_stride;
   p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
   p.remap_rows = a.remap_rows; p.remap_stride = a.remap_stride; p.remap_offset = a.remap_offset;
+  p.dbg = nullptr;
 
   auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CL>;
   static bool attr_set = false;
@@ -332,8 +333,14 @@ static int dispatch_epi(const vds_gemm_args& a, cudaStream_t s) {
 }
 
 int gemm2_dispatch(const vds_gemm_args& a, cudaStream_t s);   // gemm2.cu
+void gemm2_set_trace(long long* p);
 
 }  // namespace vds
+
+extern "C" int vds_debug_gemm2_trace(void* buf) {
+  vds::gemm2_set_trace((long long*)buf);
+  return VDS_OK;
+}
 
 extern "C" int vds_gemm(const vds_gemm_args* args, void* stream) {
   using namespace vds;

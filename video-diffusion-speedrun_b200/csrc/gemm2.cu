@@ -17,6 +17,8 @@
 
 namespace vds {
 
+long long* g_gemm2_trace = nullptr;   // tuning aid: CTA 0 accumulates wait / busy cycles per role
+
 constexpr int G2_THREADS = 320;
 constexpr int G2_BN = 256;              // tile N of the CTA pair
 constexpr int G2_A_BYTES = BM * BK * 2;           // 16 KiB
@@ -24,7 +26,7 @@ constexpr int G2_B_BYTES = (G2_BN / 2) * BK * 2;  // 16 KiB: this CTA's half of 
 constexpr int G2_STAGE = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_STAGES = 6;
 constexpr int G2_STG = 8 * 4096;
-constexpr int G2_SMEM = G2_STAGES * G2_STAGE + G2_STG + 256 + 1024;
+constexpr int G2_SMEM = G2_STAGES * G2_STAGE + G2_STG + 256 + 1024;   // [stages][staging 8 x 4 KiB][barriers]
 // shared::cluster address of the same smem offset in CTA `rank` of this cluster
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t cta_addr, uint32_t rank) {
   uint32_t r;
@@ -70,19 +72,21 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
 
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(G2_THREADS, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmDev p,
+             long long* dbg, int tma_c, int tma_c2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
-  const uint32_t bar_base = smem_base + G2_STAGES * G2_STAGE;
+  const uint32_t bar_base = smem_base + G2_STAGES * G2_STAGE + G2_STG;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (G2_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * G2_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * G2_STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * G2_STAGES + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + G2_STAGES * G2_STAGE + 8 * (2 * G2_STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + G2_STAGES * G2_STAGE + G2_STG + 8 * (2 * G2_STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crank = (int)cluster_ctarank();
@@ -159,6 +163,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      long long w_tempty = 0, w_full = 0;
+      const long long t_begin = clock64();
       for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
         const int rest = tile / m_pairs;
         const int sp = rest / n_tiles;
@@ -166,11 +172,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int kb1 = min(k_iters, kb0 + p.k_per_split);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
+        long long tq = clock64();
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        w_tempty += clock64() - tq;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * G2_BN;
         for (int kb = kb0; kb < kb1; ++kb) {
+          tq = clock64();
           mbar_wait(full_bar(stage), phase);
+          w_full += clock64() - tq;
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_addr = smem_base + stage * G2_STAGE;
@@ -190,6 +200,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      if (dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+        dbg[0] = clock64() - t_begin; dbg[1] = w_tempty; dbg[2] = w_full; dbg[3] = it;
+      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
@@ -197,12 +210,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int chalf = (warp - 2) >> 2;
     const uint32_t leader_tempty0 = mapa_rank(tempty_bar(0), 0);
     int it = 0;
+    long long e_wait = 0, e_busy = 0, e_tmem = 0, e_grp = 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
       const int mt = (tile % m_pairs) * 2 + crank;
       const int nt = (tile / m_pairs) % n_tiles;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
+      const long long te0 = clock64();
       mbar_wait(tfull_bar(acc), acc_phase);
+      const long long te1 = clock64();
+      e_wait += te1 - te0;
       tc_fence_after();
       const int row = mt * BM + q * 32 + lane;
       const uint32_t t_base = tmem_base + acc * G2_BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -219,24 +236,32 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
       } else {
-        uint8_t* stg = smem_gen + G2_STAGES * G2_STAGE + 256 + (warp - 2) * 4096;
+        uint8_t* stg = smem_gen + G2_STAGES * G2_STAGE + (warp - 2) * 4096;   // 1024-byte aligned (TMA swizzle atom)
         constexpr int GROUPS = G2_BN / 128;
 #pragma unroll 1
         for (int gi = 0; gi < GROUPS; ++gi) {
           const int cg = chalf * GROUPS + gi;
           uint32_t r0[32], r1[32];
+          const long long tg0 = clock64();
           tmem_ld32(t_base + cg * 64, r0);
           tmem_ld32(t_base + cg * 64 + 32, r1);
           tmem_ld_wait();
+          const long long tg1 = clock64();
           if (gi == GROUPS - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
           }
-          epilogue_group64<EPI>(p, stg, mt * BM + q * 32, nt * G2_BN + cg * 64, r0, r1, lane);
+          epilogue_group64<EPI>(p, stg, mt * BM + q * 32, nt * G2_BN + cg * 64, r0, r1, lane, tma_c ? &tmC : nullptr,
+                                tma_c2 ? &tmC2 : nullptr);
+          e_tmem += tg1 - tg0;
+          e_grp += clock64() - tg1;
         }
       }
+      e_busy += clock64() - te1;
     }
+    if (lane == 0) bulk_wait_group0();   // all TMA stores of this warp have completed before the CTA may exit
+    if (dbg != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0) { dbg[4] = e_wait; dbg[5] = e_busy; dbg[6] = e_tmem; dbg[7] = e_grp; }
   }
   tc_fence_before();
   __syncthreads();
@@ -261,6 +286,26 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
     r = encode_tmap_bf16(&tmB, a.B, 2, dims, strides, box);
     if (r) return r;
   }
+  // output tensor maps for the TMA-store epilogue (bf16 outputs without row remap)
+  CUtensorMap tmC = tmA, tmC2 = tmA;
+  int tma_c = 0, tma_c2 = 0;
+  // (measured: helps the plain / GELU epilogues; the aux-reading epilogues are latency-bound elsewhere and get slower)
+  if ((EPI == VDS_EPI_STORE || EPI == VDS_EPI_BIAS_GELU) && a.remap_rows == 0) {
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M}, strides[1];
+    uint32_t box[2] = {64, 32};
+    if (a.C != nullptr && a.ldc % 8 == 0 && ((uintptr_t)a.C & 15) == 0) {
+      strides[0] = (uint64_t)a.ldc * 2;
+      int r = encode_tmap_bf16(&tmC, a.C, 2, dims, strides, box);
+      if (r) return r;
+      tma_c = 1;
+    }
+    if (a.C2 != nullptr && a.ldc2 % 8 == 0 && ((uintptr_t)a.C2 & 15) == 0) {
+      strides[0] = (uint64_t)a.ldc2 * 2;
+      int r = encode_tmap_bf16(&tmC2, a.C2, 2, dims, strides, box);
+      if (r) return r;
+      tma_c2 = 1;
+    }
+  }
   GemmDev p;
   p.M = a.M; p.N = a.N; p.K = a.K;
   const int k_iters = (a.K + BK - 1) / BK;
@@ -274,6 +319,7 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
   p.gate = reinterpret_cast<const bf16*>(a.gate); p.gate_stride = a.gate_stride;
   p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
   p.remap_rows = a.remap_rows; p.remap_stride = a.remap_stride; p.remap_offset = a.remap_offset;
+  p.dbg = g_gemm2_trace;
 
   auto kern = gemm2_kernel<A_MN, B_MN, EPI>;
   static bool attr_set = false;
@@ -300,7 +346,7 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, p, g_gemm2_trace, tma_c, tma_c2);
   if (e != cudaSuccess) {
     set_error("gemm2: cluster launch failed: %s", cudaGetErrorString(e));
     return VDS_ERR_CUDA;
@@ -308,6 +354,8 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
   VDS_CHECK_LAUNCH("gemm2");
   return VDS_OK;
 }
+
+void gemm2_set_trace(long long* p) { g_gemm2_trace = p; }
 
 // Entry used by gemm.cu's dispatcher: returns VDS_ERR_UNSUPPORTED when the shape / epilogue has no 2-CTA variant.
 int gemm2_dispatch(const vds_gemm_args& a, cudaStream_t s) {

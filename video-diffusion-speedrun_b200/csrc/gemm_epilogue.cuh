@@ -23,29 +23,61 @@ struct GemmDev {
   long long gate_stride;
   int rows_per_batch;
   int remap_rows, remap_stride, remap_offset;
+  long long* dbg;   // tuning aid (nullptr in production)
 };
 
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 rounding of the outputs): the libm
-// erff costs ~4x more instructions and made the GELU epilogues, not the MMAs, the bottleneck of the MLP GEMMs.
-// Returns erf(x/sqrt2) and exp(-x^2/2) (shared by GELU and its derivative).
-__device__ __forceinline__ float erf_as(float x, float& gauss) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+// GELU(erf) and its derivative via Abramowitz-Stegun 7.1.26: 1 - erf(z) = q(z) = (a1 t + ... + a5 t^5) exp(-z^2),
+// t = 1/(1 + p z), z = |x|/sqrt2, |abs err| <= 1.5e-7 — far below the bf16 rounding of the outputs.  libm erff cost
+// ~4x more instructions and made the epilogue, not the MMAs, the bottleneck of the MLP GEMMs; MUFU rcp/ex2 are used
+// in their single-instruction approximate forms.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// returns q(|x|/sqrt2) in [0, 1] and exp(-x^2/2)
+__device__ __forceinline__ float erfc_as(float x, float& gauss) {
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  gauss = exp2f(-0.72134752044448170368f * x * x);   // exp(-x^2/2) = exp(-z^2)
-  const float e = fmaf(-poly * t, gauss, 1.0f);
-  return copysignf(e, x);
+  gauss = ex2(-0.72134752044448170368f * x * x);   // exp(-x^2/2)
+  return poly * t * gauss;
+}
+// two elements at a time on the packed fp32x2 pipe (halves the FMA-pipe issue slots of the polynomial)
+__device__ __forceinline__ float2 erfc_as2(float2 x, float2& gauss) {
+  const float kp = 0.3275911f * 0.70710678118654752440f;
+  const float2 d = fma2(make_float2(kp, kp), make_float2(fabsf(x.x), fabsf(x.y)), make_float2(1.f, 1.f));
+  const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+  float2 poly = fma2(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  poly = fma2(poly, t, make_float2(1.421413741f, 1.421413741f));
+  poly = fma2(poly, t, make_float2(-0.284496736f, -0.284496736f));
+  poly = fma2(poly, t, make_float2(0.254829592f, 0.254829592f));
+  const float2 e = mul2(mul2(x, x), make_float2(-0.72134752044448170368f, -0.72134752044448170368f));
+  gauss = make_float2(ex2(e.x), ex2(e.y));
+  return mul2(mul2(poly, t), gauss);
+}
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  float2 g;
+  const float2 h = mul2(mul2(x, make_float2(0.5f, 0.5f)), erfc_as2(x, g));
+  return make_float2(x.x >= 0.f ? x.x - h.x : h.x, x.y >= 0.f ? x.y - h.y : h.y);
+}
+__device__ __forceinline__ float2 dgelu_erf2(float2 x) {
+  float2 g;
+  const float2 hq = mul2(erfc_as2(x, g), make_float2(0.5f, 0.5f));
+  const float2 cdf = make_float2(x.x >= 0.f ? 1.0f - hq.x : hq.x, x.y >= 0.f ? 1.0f - hq.y : hq.y);
+  return fma2(mul2(x, make_float2(0.39894228040143267794f, 0.39894228040143267794f)), g, cdf);
 }
 __device__ __forceinline__ float gelu_erf(float x) {
   float g;
-  return 0.5f * x * (1.0f + erf_as(x, g));
+  const float h = 0.5f * x * erfc_as(x, g);          // x >= 0: gelu = x - h ; x < 0: gelu = h
+  return x >= 0.f ? x - h : h;
 }
 __device__ __forceinline__ float dgelu_erf(float x) {
   float g;
-  const float cdf = 0.5f * (1.0f + erf_as(x, g));
+  const float hq = 0.5f * erfc_as(x, g);
+  const float cdf = x >= 0.f ? 1.0f - hq : hq;
   return fmaf(x * 0.39894228040143267794f, g, cdf);
 }
 
@@ -119,47 +151,66 @@ __device__ __forceinline__ void unpack8(uint4 u, float (&o)[8]) {
 }
 
 // One warp, 32 rows x 64 columns [col0, col0 + 64): acc = 64 fp32 per thread (its own row).
+// tmC / tmC2 != nullptr: the staged 32 x 64 sub-tile leaves through the TMA unit (cp.async.bulk.tensor store, the
+// staging buffer's XOR swizzle IS the 128-byte TMA swizzle) instead of 8 LDS + STG per thread: per-thread global
+// stores sustain only ~32 B/clk/SM, which made the output write, not the MMAs, the limit of the K = 512 GEMMs.
 template <int EPI>
 __device__ __forceinline__ void epilogue_group64(const GemmDev& p, uint8_t* stg, int row0, int col0,
-                                                 const uint32_t (&r0)[32], const uint32_t (&r1)[32], int lane) {
+                                                 const uint32_t (&r0)[32], const uint32_t (&r1)[32], int lane,
+                                                 const void* tmC = nullptr, const void* tmC2 = nullptr) {
   RowMap rm{row0, p.M, p.remap_rows, p.remap_stride, p.remap_offset};
   const int my_row = row0 + lane;
+  const bool trace = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
+  const long long tq0 = clock64();
   if constexpr (EPI == VDS_EPI_GATE_RES || EPI == VDS_EPI_DGELU) {
     stg_load(stg, p.aux, p.ldaux, rm, col0, p.N, lane);
     __syncwarp();
   }
   uint4 keep[8];  // first output (bf16 Linear result) kept packed while the second goes through the buffer
   const int b = (EPI == VDS_EPI_GATE_RES) ? min(my_row, p.M - 1) / p.rows_per_batch : 0;
+  // per-column operands (bias, gate) for all 8 chunks are requested up front: one L2 round trip per group instead
+  // of one per chunk (the serialized loads were the longest latency chain of the epilogue)
+  uint4 braw[8], graw[8];
+  const bool has_bias = (EPI != VDS_EPI_DGELU) && p.bias != nullptr;
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     const int col = col0 + g * 8;
+    braw[g] = make_uint4(0u, 0u, 0u, 0u);
+    graw[g] = make_uint4(0u, 0u, 0u, 0u);
+    if (col < p.N) {
+      if (has_bias) braw[g] = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+      if constexpr (EPI == VDS_EPI_GATE_RES)
+        graw[g] = __ldg(reinterpret_cast<const uint4*>(p.gate + (long long)b * p.gate_stride + col));
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]);
-    const bool col_ok = col < p.N;
-    if constexpr (EPI != VDS_EPI_DGELU) {
-      if (p.bias != nullptr && col_ok) {
-        float bb[8];
-        ld8_bf16(p.bias + col, bb);
+    if (has_bias) {
+      float bb[8];
+      unpack8(braw[g], bb);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += bb[j];
-      }
+      for (int j = 0; j < 8; ++j) acc[j] += bb[j];
     }
     uint8_t* slot = stg + stg_off(lane, g);
     if constexpr (EPI == VDS_EPI_STORE) {
       *reinterpret_cast<uint4*>(slot) = pack8(acc);
     } else if constexpr (EPI == VDS_EPI_BIAS_GELU) {
       float act[8];
+      keep[g] = pack8(acc);                               // bf16 Linear output (what the reference's GELU sees)
+      unpack8(keep[g], acc);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[j] = bf16_round(acc[j]);
-        act[j] = gelu_erf(acc[j]);
+      for (int j = 0; j < 8; j += 2) {
+        const float2 a2 = gelu_erf2(make_float2(acc[j], acc[j + 1]));
+        act[j] = a2.x;
+        act[j + 1] = a2.y;
       }
-      keep[g] = pack8(acc);
       *reinterpret_cast<uint4*>(slot) = pack8(act);
     } else if constexpr (EPI == VDS_EPI_GATE_RES) {
-      float g8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, x8[8], o8[8];
-      if (col_ok) ld8_bf16(p.gate + (long long)b * p.gate_stride + col, g8);
+      float g8[8], x8[8], o8[8];
+      unpack8(graw[g], g8);
       unpack8(*reinterpret_cast<const uint4*>(slot), x8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -172,12 +223,37 @@ __device__ __forceinline__ void epilogue_group64(const GemmDev& p, uint8_t* stg,
       float h8[8];
       unpack8(*reinterpret_cast<const uint4*>(slot), h8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] *= dgelu_erf(h8[j]);
+      for (int j = 0; j < 8; j += 2) {
+        const float2 d2 = mul2(make_float2(acc[j], acc[j + 1]), dgelu_erf2(make_float2(h8[j], h8[j + 1])));
+        acc[j] = d2.x;
+        acc[j + 1] = d2.y;
+      }
       *reinterpret_cast<uint4*>(slot) = pack8(acc);
     }
   }
+  const long long tq1 = clock64();
+  const bool tma_out = (EPI == VDS_EPI_STORE || EPI == VDS_EPI_DGELU) ? tmC != nullptr : tmC2 != nullptr;
+  if (tma_out) fence_proxy_async_smem();
   __syncwarp();
-  if constexpr (EPI == VDS_EPI_STORE || EPI == VDS_EPI_DGELU) {
+  const long long tq2 = clock64();
+  if (tma_out) {
+    const uint32_t stg_s = smem_u32(stg);
+    if constexpr (EPI == VDS_EPI_STORE || EPI == VDS_EPI_DGELU) {
+      if (lane == 0) { tma_store_2d(tmC, stg_s, col0, row0); bulk_commit_group(); }
+    } else {
+      if (lane == 0) { tma_store_2d(tmC2, stg_s, col0, row0); bulk_commit_group(); }
+      if (p.C != nullptr) {
+        if (lane == 0) bulk_wait_group_read0();     // the TMA unit has read the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(stg + stg_off(lane, g)) = keep[g];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { tma_store_2d(tmC, stg_s, col0, row0); bulk_commit_group(); }
+      }
+    }
+    if (lane == 0) bulk_wait_group_read0();         // staging reusable by the next group
+  } else if constexpr (EPI == VDS_EPI_STORE || EPI == VDS_EPI_DGELU) {
     stg_store(stg, reinterpret_cast<bf16*>(p.C), p.ldc, rm, col0, p.N, lane, EPI == VDS_EPI_STORE);
   } else {
     stg_store(stg, reinterpret_cast<bf16*>(p.C2), p.ldc2, rm, col0, p.N, lane, false);
@@ -189,7 +265,14 @@ __device__ __forceinline__ void epilogue_group64(const GemmDev& p, uint8_t* stg,
       stg_store(stg, reinterpret_cast<bf16*>(p.C), p.ldc, rm, col0, p.N, lane, false);
     }
   }
+  const long long tq3 = clock64();
   __syncwarp();
+  if (trace) {
+    atomicAdd((unsigned long long*)p.dbg + 8, (unsigned long long)(tq1 - tq0));
+    atomicAdd((unsigned long long*)p.dbg + 9, (unsigned long long)(tq2 - tq1));
+    atomicAdd((unsigned long long*)p.dbg + 10, (unsigned long long)(tq3 - tq2));
+    atomicAdd((unsigned long long*)p.dbg + 11, (unsigned long long)(clock64() - tq3));
+  }
 }
 
 // One thread handles 32 consecutive columns [col0, col0+32) of output row `row`.
