@@ -269,7 +269,9 @@ def run_ours(args):
             "step_frac_of_bf16_peak": step_flops / (step_ms * 1e-3) / 1e12 / peak,
             "roofline": {"kernel": "attn_bwd_kernel (self-attention backward, L=%d)" % Lr, "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": pk_src + " (bf16_tflops_sustained)",
+                         "traffic": 123.7e6 if args.workload == "debug-8k" else None,
+                         "traffic_note": "dram__bytes_read+write per launch, ncu --set full (profiles/r1_ncu_attention_full.md)",
+                         "peak_source": pk_src + " (bf16_tflops_sustained)",
                          "kernel_ms": kern_ms, "launches_timed": len(prof),
                          "kernel_share_of_step": kern_ms * depth / step_ms},
             "e2e": {"value": world * B * N / (e2e_ms * 1e-3), "unit": "latent tokens/s", "ms_per_step": e2e_ms,

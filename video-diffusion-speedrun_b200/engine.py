@@ -64,6 +64,11 @@ class Ctx:
 
 
 def forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise=None):
+    with ops.pinned_stream():
+        return _forward(model, P, x, context, timesteps, save, rope_starts, noise)
+
+
+def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise=None):
     """Returns (out [B,C,T,H,W] bf16, ctx or None).  With `noise`, `x` is the clean latent and
     z_t = x*(1-t) + noise*t (train.py:115-116) is formed inside the patch gather."""
     dev = x.device
@@ -344,11 +349,13 @@ def run_backward(model, P, c, dout, dtypes):
         flat.begin_backward()
         sink = GradSink(model, dout.device, flat.grad_views)
         sink.on_block_done = flat.block_backward_done
-        backward(model, P, c, dout, sink)
+        with ops.pinned_stream():
+            backward(model, P, c, dout, sink)
         flat.end_backward()
         return tuple(None for _ in names)
     sink = GradSink(model, dout.device)
-    backward(model, P, c, dout, sink)
+    with ops.pinned_stream():
+        backward(model, P, c, dout, sink)
     grads = []
     for n, dt in zip(names, dtypes):
         g = sink.g.get(n)

@@ -15,8 +15,26 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+# The engine pins the launch stream for the duration of one forward / backward (saves a
+# torch.cuda.current_stream() lookup per launch: ~1100 of them per train step).
+_PINNED_STREAM = None
+
+
+class pinned_stream:
+    def __enter__(self):
+        global _PINNED_STREAM
+        self.prev = _PINNED_STREAM
+        _PINNED_STREAM = torch.cuda.current_stream().cuda_stream
+        return self
+
+    def __exit__(self, *exc):
+        global _PINNED_STREAM
+        _PINNED_STREAM = self.prev
+        return False
+
+
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(_PINNED_STREAM if _PINNED_STREAM is not None else torch.cuda.current_stream().cuda_stream)
 
 
 def _chk_bf16(*ts):
@@ -78,7 +96,7 @@ def _p(t):
 
 
 def _s():
-    return torch.cuda.current_stream().cuda_stream
+    return _PINNED_STREAM if _PINNED_STREAM is not None else torch.cuda.current_stream().cuda_stream
 
 
 def patchify(x, p, pt, noise=None, t=None, out=None):

@@ -106,8 +106,9 @@ class FlatShards:
         f32 = dict(device=self.device, dtype=torch.float32)
         b16 = dict(device=self.device, dtype=torch.bfloat16)
         self.master = torch.zeros(lay.shard_total, **f32)
-        self.shard16 = torch.zeros(lay.shard_total, **b16)
         self.full16 = torch.zeros(lay.full_total, **b16)
+        # world size 1: the bf16 shard IS the gathered buffer (AdamW writes the compute copy in place, no gather copy)
+        self.shard16 = self.full16 if self.world == 1 else torch.zeros(lay.shard_total, **b16)
         self.gfull = torch.zeros(lay.full_total, **f32)
         self.gshard = self.gfull if self.world == 1 else torch.zeros(lay.shard_total, **f32)
         # move the module's values into the master shard; re-point the module's Parameters at it
@@ -189,6 +190,8 @@ class FlatShards:
     def gather_params(self):
         """All-gather every group's bf16 shard on the side stream (root group first, then block 0, 1, ...)."""
         order = [self.depth] + list(range(self.depth))
+        if self.world == 1:
+            return  # shard16 aliases full16
         if not self.use_cuda:
             for g in order:
                 fs, ss = self._group_slices(g)
