@@ -25,3 +25,16 @@ def test_denoise_loop_matches_oracle(cuda_dev):
     err = (got - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
     cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
     assert cos > 0.995 and err < 0.1, (cos, err)
+
+
+def test_context_kv_cache_is_bit_identical(cuda_dev):
+    from vds_b200.sampling.sample import denoise
+    fx, cfg, model, (latent, noise, context, t) = golden_case("tiny_nobias")
+    model = model.to(cuda_dev, torch.bfloat16).eval()
+    lat0, ctx = noise.to(cuda_dev), context.to(cuda_dev)
+    torch.manual_seed(3)
+    a = denoise(model, ctx, inference_steps=3, latents=lat0, device=cuda_dev, cache_context_kv=False)
+    torch.manual_seed(3)
+    b = denoise(model, ctx, inference_steps=3, latents=lat0, device=cuda_dev, cache_context_kv=True)
+    assert torch.equal(a, b)
+    assert model._ckv_cache is None

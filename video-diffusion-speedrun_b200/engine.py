@@ -137,7 +137,15 @@ def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise
             n2, rstd2 = ops.rmsnorm_mod_fwd(X1, B, Lr, h, scale=scale_ca, shift=shift_ca,
                                             weight=P.get(pre + "norm2.weight"), want_rstd=save)
             qc = ops.gemm(n2, P[pre + "q_cross.weight"], bias=P.get(pre + "q_cross.bias"))
-            ckv = ops.gemm(ctx2d, P[pre + "context_kv.weight"], bias=P.get(pre + "context_kv.bias"))
+            ckv = None
+            cache = getattr(model, "_ckv_cache", None) if not save else None
+            if cache is not None:   # inference: context_kv(context) depends only on the prompt, not on the step (§8f n2)
+                key = (i, ctx2d.data_ptr(), ctx2d._version, tuple(ctx2d.shape))
+                ckv = cache.get(key)
+            if ckv is None:
+                ckv = ops.gemm(ctx2d, P[pre + "context_kv.weight"], bias=P.get(pre + "context_kv.bias"))
+                if cache is not None:
+                    cache[key] = ckv
             ca, lse2 = ops.attn_fwd(qc, ckv[:, :h], ckv[:, h:], B, nh, Lr, Lc, want_lse=save)
             o2, X2 = ops.gemm(ca, P[pre + "cross_proj.weight"], epilogue=L.EPI_GATE_RES, aux=X1, gate=gate_ca,
                               rows_per_batch=Lr)

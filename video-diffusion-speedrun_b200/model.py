@@ -189,7 +189,15 @@ class DiT(nn.Module):
         self.paramstatus = {}
         for n, p in self.named_parameters():
             self.paramstatus[n] = {"shape": p.shape, "requires_grad": p.requires_grad}
+        self._ckv_cache = None
         self._flat = None  # set by apply_fsdp (shard.FlatShards): flat master / gathered bf16 / gradient buffers
+
+    def context_kv_cache(self, enabled=True):
+        """Forward-only runs (sampling): keep every block's ``context_kv(context)`` ([B*Lc, 2h] bf16) keyed by the context
+        tensor, so the K = 4096 GEMM runs once per prompt instead of once per denoising step and block.  Results are
+        bit-identical (same kernel, same inputs).  Call with ``False`` (or change the weights) to drop the cache."""
+        self._ckv_cache = {} if enabled else None
+        return self
 
     def _param_view(self):
         """bf16 compute parameters: views into the gathered flat buffers when sharded, else (cast) copies."""

@@ -13,7 +13,7 @@ def shift_time(t, alpha=8.0):
 
 @torch.no_grad()
 def denoise(model, prompt_embeds, latent_shape=(1, 16, 16, 64, 64), inference_steps=50, cfg_scale=6.0, seed=42,
-            device="cuda", dtype=torch.bfloat16, latents=None, on_step=None):
+            device="cuda", dtype=torch.bfloat16, latents=None, on_step=None, cache_context_kv=True):
     """sample.py:92-146.  Returns acc_latents (fp32).  Two separate model calls per step (cond / uncond), each drawing
     its own RoPE offsets from the global CPU generator, exactly like the reference."""
     prompt_embeds = prompt_embeds.to(device=device, dtype=dtype)
@@ -22,6 +22,8 @@ def denoise(model, prompt_embeds, latent_shape=(1, 16, 16, 64, 64), inference_st
         generator = torch.Generator(device=device).manual_seed(seed)         # sample.py:108
         latents = torch.randn(latent_shape, device=device, dtype=dtype, generator=generator)
     acc_latents = latents.to(dtype=torch.float32)
+    if cache_context_kv and hasattr(model, "context_kv_cache"):
+        model.context_kv_cache(True)     # prompt / negative embeddings are constant over the loop
     for i in range(inference_steps, 0, -1):
         t = shift_time(i / inference_steps)
         t_next = shift_time((i - 1) / inference_steps)
@@ -35,4 +37,6 @@ def denoise(model, prompt_embeds, latent_shape=(1, 16, 16, 64, 64), inference_st
         latents = acc_latents.to(dtype=dtype)
         if on_step is not None:
             on_step(i, acc_latents)
+    if cache_context_kv and hasattr(model, "context_kv_cache"):
+        model.context_kv_cache(False)
     return acc_latents
