@@ -159,3 +159,17 @@ def test_sampling_width_forward_only(cuda_dev):
         ref = O.dit_forward(P, cfg, latent.float(), context.float(), t.float(), rope_starts=starts,
                             table_dtype=torch.bfloat16)
     assert (out.float() - ref).abs().max().item() <= 3e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("B,latent_thw,Lc", [(1, (2, 2, 2), 8), (3, (2, 6, 10), 40), (1, (6, 10, 14), 512)])
+def test_ragged_and_tiny_shapes_vs_oracle(cuda_dev, B, latent_thw, Lc):
+    """Edge cases: a single patch token (L = 17), sequence lengths that end inside a tile (L = 31, 121), batch 1 / 3,
+    short and full-length contexts."""
+    cfg = dict(in_channels=16, patch_size=2, time_patch_size=2, hidden_size=256, depth=2, num_heads=2, mlp_ratio=4.0,
+               cross_attn_input_size=64, residual_v=True, train_bias_and_rms=True, use_rope=True)
+    model = build_model(cfg, 0, 1).to(cuda_dev)
+    latent, noise, context, t = [a.to(cuda_dev) for a in O.make_inputs(cfg, B, latent_thw, Lc, 64, 8)]
+    loss, _, grads = _cuda_step(model, latent, noise, context, t, 13, fused=True)
+    thw = tuple(d // 2 for d in latent_thw)
+    rl, _, rg = _oracle_step(model, cfg, latent, noise, context, t, 13, thw, torch.float32, cuda_dev)
+    _compare(f"B={B} thw={latent_thw}", loss, grads, rl, rg)
