@@ -171,12 +171,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int valid = p.Lk - j * 128;             // columns >= valid are padding (last tile only)
       mbar_wait(s_full + 8 * t, j & 1);
       tc_fence_after();
+      // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is reduced
       float mx = -INFINITY;
-#pragma unroll 1
+      uint32_t va[32], vb[32];
+      tmem_ld32(tS, va);
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + c * 32, v);
+        uint32_t (&v)[32] = (c & 1) ? vb : va;
         tmem_ld_wait();
+        if (c < 3) tmem_ld32(tS + (c + 1) * 32, (c & 1) ? va : vb);
         if (valid >= 128) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
@@ -208,12 +211,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       l_run *= alpha;
       float sum = 0.f;
       const float nm = -m_run;
-#pragma unroll 1
+      tmem_ld32(tS, va);
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
+        uint32_t (&v)[32] = (c & 1) ? vb : va;
         uint32_t pk[16];
-        tmem_ld32(tS + c * 32, v);
         tmem_ld_wait();
+        if (c < 3) tmem_ld32(tS + (c + 1) * 32, (c & 1) ? va : vb);
         if (valid >= 128) {
           float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
