@@ -190,8 +190,14 @@ def run_ours(args):
     latent, noise, context, t = latent_h.to(dev), noise_h.to(dev), context_h.to(dev), t_h.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    stepper = None
+    if args.graph and world == 1:
+        stepper = train.GraphedTrainStep(model, opt, latent.shape, context.shape, device=dev, warmup=2)
+
     def step(i, lat, ctx):
         torch.manual_seed(i)  # RoPE offset draws (model.py:224-226)
+        if stepper is not None:
+            return stepper(lat, ctx, t, noise)
         opt.zero_grad()
         loss, _ = train.forward(model, lat, ctx, t=t, noise=noise)
         loss.backward()
@@ -211,7 +217,8 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     # ---- timed region 1: inputs resident in HBM; dominant kernel timed live with events on the launch stream
-    ops.PROFILE["attn_bwd_self"] = []
+    if stepper is None:
+        ops.PROFILE["attn_bwd_self"] = []
     launches0 = lib.launch_count()
     evs = []
     barrier()
@@ -225,7 +232,7 @@ def run_ours(args):
     barrier()
     launches = lib.launch_count() - launches0
     step_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
-    prof = ops.PROFILE.pop("attn_bwd_self")
+    prof = ops.PROFILE.pop("attn_bwd_self", [])
     kern_ms = sum(a.elapsed_time(b) for a, b in prof) / max(1, len(prof))
     ops.PROFILE.clear()
 
@@ -246,6 +253,30 @@ def run_ours(args):
     barrier()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs) / args.steps
     sampler.stop_flag = True
+
+    # ---- extra (world size 1, eager runs only): the same step replayed from a CUDA graph (train.GraphedTrainStep)
+    graph_ms = None
+    if world == 1 and stepper is None and not args.no_graph_extra:
+        try:
+            gstep = train.GraphedTrainStep(model, opt, latent.shape, context.shape, device=dev, warmup=1)
+            for i in range(3):
+                torch.manual_seed(1000 + i)
+                gstep(latent, context, t, noise)
+            barrier()
+            gev = []
+            for i in range(args.steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.manual_seed(2000 + i)
+                gstep(latent, context, t, noise)
+                e1.record()
+                gev.append((e0, e1))
+            barrier()
+            graph_ms = sum(a.elapsed_time(b) for a, b in gev) / args.steps
+        except Exception as ex:  # the extra must never take the bench line down
+            graph_ms = None
+            sys.stderr.write(f"graph extra skipped: {ex}\n")
 
     tm = torch.tensor([step_ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -276,7 +307,11 @@ def run_ours(args):
                          "kernel_share_of_step": kern_ms * depth / step_ms},
             "e2e": {"value": world * B * N / (e2e_ms * 1e-3), "unit": "latent tokens/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss_host},
-            "gpu_launches": launches, "clocks": sampler.summary(),
+            "gpu_launches": launches if stepper is None else stepper.launches_per_step * args.steps,
+            "cuda_graph": stepper is not None, "clocks": sampler.summary(),
+            "graph_replay": None if graph_ms is None else {
+                "ms_per_step": graph_ms, "value": world * B * N / (graph_ms * 1e-3), "unit": "latent tokens/s",
+                "note": "same step captured once and replayed as ONE CUDA graph (train.GraphedTrainStep); extra, not the headline"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_step(args.workload, steps=2, warmup=1)
@@ -297,6 +332,8 @@ def main():
     ap.add_argument("--workload", default="debug-8k", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="world size 1: capture the whole step in a CUDA graph")
+    ap.add_argument("--no-graph-extra", action="store_true", help="skip the extra graph-replay measurement")
     ap.add_argument("--depth", type=int, default=0, help="profiling only: override the model depth (NOT a bench line)")
     args = ap.parse_args()
     if args.depth > 0:

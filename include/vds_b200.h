@@ -93,7 +93,8 @@ int vds_unpatchify(const void* src, void* dst, int B, int C, int T, int H, int W
 /* cos/sin rows [L, D] fp32 from the persistent tables [tmax,hmax,wmax,D] (fp32 or bf16) at the random start
  * offsets; rows < n_reg are the identity rotation; rows flattened "(t h w)".           model.py:219-263 */
 int vds_rope_rows(const void* tcos, const void* tsin, int table_is_bf16, float* ocos, float* osin, int L, int D,
-                  int n_reg, int Tp, int Hp, int Wp, int st, int sh, int sw, int hmax, int wmax, void* stream);
+                  int n_reg, int Tp, int Hp, int Wp, int st, int sh, int sw, int hmax, int wmax, const int* starts_dev,
+                  void* stream);   /* starts_dev != NULL: (t,h,w) offsets read from device memory (graph replays) */
 /* [cos(t f_i) | sin(t f_i)], bf16 out.                                                  model.py:12-22 */
 int vds_timestep_embedding(const void* t, void* out, int B, int dim, float max_period, void* stream);
 /* SiLU and its backward (nn.SiLU at model.py:90,320,340). */
@@ -156,7 +157,7 @@ int vds_loss_fwd_bwd(const void* x, const void* noise, const void* out, void* d_
 int vds_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const int64_t* chunk_start,
               const int32_t* chunk_len, const int32_t* chunk_group, int n_chunks, const float* lr_host,
               const float* wd_host, int n_groups, float beta1, float beta2, float eps, int step, float grad_scale,
-              void* stream);
+              const float* hyper_dev, void* stream); /* hyper_dev != NULL: [lr[16]|wd[16]|bc1|sqrt(bc2)] on the device */
 
 #ifdef __cplusplus
 }

@@ -3,7 +3,7 @@
 TAG=${1:-r1}
 EXTRA=${2:-}
 ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline $EXTRA > gpurun_out/ncu_bench_$TAG.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph-extra $EXTRA > gpurun_out/ncu_bench_$TAG.log 2>&1
 python - <<PY
 import csv, collections, sys
 rows = list(csv.reader(open("gpurun_out/launches_$TAG.csv", errors="ignore")))

@@ -74,3 +74,46 @@ def test_stock_torch_adamw_on_flat_params(cuda_dev):
         opt.step()
         losses.append(loss.item())
     assert losses[2] < losses[0], losses   # it trains, i.e. the bf16 compute copy follows the master weights
+
+
+def test_graphed_train_step_matches_eager(cuda_dev):
+    """CUDA-graph captured step (device-side RoPE offsets + optimizer scalars) == eager step, step for step."""
+    from vds_b200 import train
+    from vds_b200.model import apply_fsdp
+    from vds_b200.optim import FusedAdamW
+    results = []
+    for graphed in (False, True):
+        fx, cfg, model, (latent, noise, context, t) = golden_case("tiny_bias")
+        model = apply_fsdp(model.to(cuda_dev), torch.bfloat16, torch.float32)
+        groups, _ = model.get_mup_setup(2 ** -7, 1e-1, CONST)
+        opt = FusedAdamW(groups, betas=(0.95, 0.99), flat=model._flat)
+        latent, noise, context, t = [a.to(cuda_dev) for a in (latent, noise, context, t)]
+        stepper = train.GraphedTrainStep(model, opt, latent.shape, context.shape, device=cuda_dev, warmup=1) if graphed else None
+        losses = []
+        for step in range(4):
+            torch.manual_seed(100 + step)
+            for g in opt.param_groups:          # a moving learning rate, as a scheduler would produce
+                g["lr"] = g["lr"] * 0.9
+            if graphed:
+                loss = stepper(latent, context, t, noise)
+            else:
+                opt.zero_grad()
+                loss, _ = train.forward(model, latent, context, t=t, noise=noise)
+                loss.backward()
+                opt.step()
+            losses.append(loss.item())
+        torch.cuda.synchronize()
+        results.append((losses, {n: p.detach().clone() for n, p in model.named_parameters()}))
+        init = {n: p.detach().clone() for n, p in golden_case("tiny_bias")[2].named_parameters()}
+    (l0, p0), (l1, p1) = results
+    assert l1[2] != l1[1]                         # the replayed steps really see new offsets / updated weights
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 2e-3 * abs(a), (l0, l1)
+    # Adam turns near-zero gradients into +-lr steps, and the fp32 atomics of split-K / column sums are unordered,
+    # so two runs agree on the update direction, not bit for bit: compare the accumulated updates.
+    for n in p0:
+        u0, u1 = (p0[n] - init[n].to(cuda_dev)).flatten(), (p1[n] - init[n].to(cuda_dev)).flatten()
+        if u0.abs().max().item() == 0:
+            assert u1.abs().max().item() == 0, n
+            continue
+        assert cos_sim(u0, u1) > 0.98, (n, cos_sim(u0, u1))

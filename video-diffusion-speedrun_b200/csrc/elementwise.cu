@@ -86,7 +86,12 @@ __global__ void unpatchify_kernel(const bf16* __restrict__ src, bf16* __restrict
 template <typename TT>
 __global__ void rope_rows_kernel(const TT* __restrict__ tcos, const TT* __restrict__ tsin, float* __restrict__ ocos,
                                  float* __restrict__ osin, int L, int D, int n_reg, int Tp, int Hp, int Wp,
-                                 int st, int sh, int sw, int hmax, int wmax) {
+                                 int st, int sh, int sw, int hmax, int wmax, const int* __restrict__ starts_dev) {
+  if (starts_dev != nullptr) {   // CUDA-graph replays: the (t, h, w) offsets of this step live in device memory
+    st = starts_dev[0];
+    sh = starts_dev[1];
+    sw = starts_dev[2];
+  }
   const long long total = (long long)L * D;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -695,17 +700,18 @@ int vds_unpatchify(const void* src, void* dst, int B, int C, int T, int H, int W
 }
 
 int vds_rope_rows(const void* tcos, const void* tsin, int table_is_bf16, float* ocos, float* osin, int L, int D,
-                  int n_reg, int Tp, int Hp, int Wp, int st, int sh, int sw, int hmax, int wmax, void* stream) {
+                  int n_reg, int Tp, int Hp, int Wp, int st, int sh, int sw, int hmax, int wmax, const int* starts_dev,
+                  void* stream) {
   VDS_CHECK_ARG(L == n_reg + Tp * Hp * Wp, "rope_rows: L=%d != %d + %d*%d*%d", L, n_reg, Tp, Hp, Wp);
   const long long total = (long long)L * D;
   const int grid = min(ceil_div(total, 256), num_sms() * 16);
   if (table_is_bf16)
     rope_rows_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)tcos, (const bf16*)tsin, ocos, osin,
-                                                                  L, D, n_reg, Tp, Hp, Wp, st, sh, sw, hmax, wmax);
+                                                                  L, D, n_reg, Tp, Hp, Wp, st, sh, sw, hmax, wmax, starts_dev);
   else
     rope_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)tcos, (const float*)tsin, ocos,
                                                                    osin, L, D, n_reg, Tp, Hp, Wp, st, sh, sw, hmax,
-                                                                   wmax);
+                                                                   wmax, starts_dev);
   VDS_CHECK_LAUNCH("rope_rows");
   return VDS_OK;
 }

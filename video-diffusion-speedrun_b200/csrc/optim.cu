@@ -61,20 +61,25 @@ struct AdamArgs {
   const long long* chunk_start; const int* chunk_len; const int* chunk_group;
   float lr[16]; float wd[16];
   float beta1, beta2, eps, bc1, bc2_sqrt, gscale;
+  const float* hyper_dev;   // optional [lr[16] | wd[16] | bc1 | bc2_sqrt] in device memory (CUDA-graph replays)
 };
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a) {
   const int c = blockIdx.x;
   const long long s = a.chunk_start[c];
   const int n = a.chunk_len[c];
   const int grp = a.chunk_group[c];
-  const float lr = a.lr[grp], decay = 1.0f - lr * a.wd[grp], step = lr / a.bc1;
+  float lr = a.lr[grp], wd = a.wd[grp], bc1 = a.bc1, bc2_sqrt = a.bc2_sqrt;
+  if (a.hyper_dev != nullptr) {
+    lr = a.hyper_dev[grp]; wd = a.hyper_dev[16 + grp]; bc1 = a.hyper_dev[32]; bc2_sqrt = a.hyper_dev[33];
+  }
+  const float decay = 1.0f - lr * wd, step = lr / bc1;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const long long k = s + i;
     const float g = a.g[k] * a.gscale;
     float p = a.p[k] * decay;
     const float m = a.beta1 * a.m[k] + (1.0f - a.beta1) * g;
     const float v = a.beta2 * a.v[k] + (1.0f - a.beta2) * g * g;
-    p -= step * m / (sqrtf(v) / a.bc2_sqrt + a.eps);
+    p -= step * m / (sqrtf(v) / bc2_sqrt + a.eps);
     a.p[k] = p; a.m[k] = m; a.v[k] = v;
     if (a.p_bf16 != nullptr) a.p_bf16[k] = __float2bfloat16_rn(p);
   }
@@ -105,7 +110,7 @@ int vds_loss_fwd_bwd(const void* x, const void* noise, const void* out, void* d_
 int vds_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const int64_t* chunk_start,
               const int32_t* chunk_len, const int32_t* chunk_group, int n_chunks, const float* lr_host,
               const float* wd_host, int n_groups, float beta1, float beta2, float eps, int step, float grad_scale,
-              void* stream) {
+              const float* hyper_dev, void* stream) {
   VDS_CHECK_ARG(n_groups >= 1 && n_groups <= 16, "adamw: 1..16 param groups supported (got %d)", n_groups);
   VDS_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
   if (n_chunks == 0) return VDS_OK;
@@ -117,6 +122,7 @@ int vds_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const 
   a.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   a.gscale = grad_scale;
+  a.hyper_dev = hyper_dev;
   adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(a);
   VDS_CHECK_LAUNCH("adamw");
   return VDS_OK;

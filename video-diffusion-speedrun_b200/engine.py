@@ -63,12 +63,12 @@ class Ctx:
     pass
 
 
-def forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise=None):
+def forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise=None, rope_starts_dev=None):
     with ops.pinned_stream():
-        return _forward(model, P, x, context, timesteps, save, rope_starts, noise)
+        return _forward(model, P, x, context, timesteps, save, rope_starts, noise, rope_starts_dev)
 
 
-def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise=None):
+def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise=None, rope_starts_dev=None):
     """Returns (out [B,C,T,H,W] bf16, ctx or None).  With `noise`, `x` is the clean latent and
     z_t = x*(1-t) + noise*t (train.py:115-116) is formed inside the patch gather."""
     dev = x.device
@@ -100,9 +100,12 @@ def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise
              remap=(N, Lr, N_REG))
 
     # ---- RoPE rows : a4
-    if rope_starts is None:
+    if rope_starts_dev is not None:
+        rope_starts = (0, 0, 0)          # graph capture: the offsets are read from device memory at replay time
+    elif rope_starts is None:
         rope_starts = draw_rope_starts(model.rope, (Tp, Hp, Wp))
-    cos, sin = ops.rope_rows(model.rope.freqs_hwt_cos, model.rope.freqs_hwt_sin, (Tp, Hp, Wp), rope_starts, N_REG)
+    cos, sin = ops.rope_rows(model.rope.freqs_hwt_cos, model.rope.freqs_hwt_sin, (Tp, Hp, Wp), rope_starts, N_REG,
+                             starts_dev=rope_starts_dev)
 
     # ---- time embedding : a5
     temb0 = ops.timestep_embedding(t_bf, h)

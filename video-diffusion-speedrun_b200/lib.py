@@ -51,7 +51,7 @@ _SIGNATURES = {
     "vds_gemm": [ctypes.POINTER(GemmArgs), vp],
     "vds_patchify": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "vds_unpatchify": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
-    "vds_rope_rows": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "vds_rope_rows": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp],
     "vds_timestep_embedding": [vp, vp, i32, i32, f32, vp],
     "vds_silu": [vp, vp, i64, vp],
     "vds_silu_bwd": [vp, vp, vp, i64, vp],
@@ -70,7 +70,7 @@ _SIGNATURES = {
     "vds_debug_attn_bwd_trace": [vp],
     "vds_debug_gemm2_trace": [vp],
     "vds_loss_fwd_bwd": [vp, vp, vp, vp, vp, vp, i32, i64, f32, vp, vp],
-    "vds_adamw": [vp, vp, vp, vp, vp, vp, vp, vp, i32, fp, fp, i32, f32, f32, f32, i32, f32, vp],
+    "vds_adamw": [vp, vp, vp, vp, vp, vp, vp, vp, i32, fp, fp, i32, f32, f32, f32, i32, f32, vp, vp],
 }
 
 _lib = None

@@ -124,7 +124,7 @@ def unpatchify(y, B, C, T, H, W, p, pt, to_tokens=False, out=None):
     return out
 
 
-def rope_rows(tcos, tsin, thw, starts, n_reg):
+def rope_rows(tcos, tsin, thw, starts, n_reg, starts_dev=None):
     """Gather cos/sin rows [L, D] (fp32) from the persistent tables at (start_t, start_h, start_w)."""
     Tp, Hp, Wp = thw
     st, sh, sw = starts
@@ -134,7 +134,8 @@ def rope_rows(tcos, tsin, thw, starts, n_reg):
     ocos = torch.empty((Lr, D), device=tcos.device, dtype=torch.float32)
     osin = torch.empty_like(ocos)
     L.check(L.lib().vds_rope_rows(_p(tcos), _p(tsin), int(tcos.dtype == torch.bfloat16), _p(ocos), _p(osin), Lr, D,
-                                  n_reg, Tp, Hp, Wp, st, sh, sw, tcos.shape[1], tcos.shape[2], _s()), "vds_rope_rows")
+                                  n_reg, Tp, Hp, Wp, st, sh, sw, tcos.shape[1], tcos.shape[2], _p(starts_dev), _s()),
+            "vds_rope_rows")
     return ocos, osin
 
 

@@ -34,6 +34,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self.m = torch.zeros_like(flat.master)
         self.v = torch.zeros_like(flat.master)
         self._step = 0
+        self.hyper_dev = None   # set by train.GraphedTrainStep: device copy of [lr | wd | bc1 | sqrt(bc2)]
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -48,9 +49,18 @@ class FusedAdamW(torch.optim.Optimizer):
         L.check(L.lib().vds_adamw(flat.master.data_ptr(), flat.gshard.data_ptr(), self.m.data_ptr(),
                                   self.v.data_ptr(), flat.shard16.data_ptr(), self.chunk_start.data_ptr(),
                                   self.chunk_len.data_ptr(), self.chunk_group.data_ptr(), self.n_chunks, lr, wd, n,
-                                  b1, b2, eps, self._step, 1.0, torch.cuda.current_stream().cuda_stream), "vds_adamw")
+                                  b1, b2, eps, self._step, 1.0,
+                                  self.hyper_dev.data_ptr() if self.hyper_dev is not None else None,
+                                  torch.cuda.current_stream().cuda_stream), "vds_adamw")
         flat.gather_params()  # side stream; the next forward waits per group
         return None
+
+    def hyper_values(self, step):
+        """[lr[16] | wd[16] | bc1 | sqrt(bc2)] for optimizer step `step` (1-based) from the current param_groups."""
+        b1, b2 = self.param_groups[0]["betas"]
+        lr = [float(g["lr"]) for g in self.param_groups] + [0.0] * (16 - len(self.param_groups))
+        wd = [float(g["weight_decay"]) for g in self.param_groups] + [0.0] * (16 - len(self.param_groups))
+        return lr + wd + [1.0 - b1 ** step, (1.0 - b2 ** step) ** 0.5]
 
     def zero_grad(self, set_to_none=True):
         # the flat gradient buffer is zeroed by the next backward; dropping .grad marks "fresh" (shard.py)

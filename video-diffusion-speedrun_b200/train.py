@@ -20,9 +20,9 @@ class TrainStepFunction(torch.autograd.Function):
     its gradient come from one fused reduction kernel, the model backward is the hand-written engine."""
 
     @staticmethod
-    def forward(ctx, model, need, latent, noise, context, t, *params):
+    def forward(ctx, model, need, latent, noise, context, t, starts_dev, *params):
         P = model._param_view()
-        out, c = engine.forward(model, P, latent, context, t, save=need, noise=noise)
+        out, c = engine.forward(model, P, latent, context, t, save=need, noise=noise, rope_starts_dev=starts_dev)
         loss, _, lb = ops.loss_fwd_bwd(latent, noise, out, want_grad=False, want_batch=True)
         ctx.model, ctx.P, ctx.c = model, P, c
         ctx.saved = (latent, noise, out)
@@ -38,10 +38,10 @@ class TrainStepFunction(torch.autograd.Function):
         _, d_out, _ = ops.loss_fwd_bwd(latent, noise, out, want_grad=True, want_loss=False, grad_scale_dev=g)
         grads = engine.run_backward(ctx.model, ctx.P, ctx.c, d_out, ctx.dtypes)
         ctx.c = None
-        return (None, None, None, None, None, None) + grads
+        return (None, None, None, None, None, None, None) + grads
 
 
-def forward(dit_model, latent, caption_encoded, generator=None, t=None, noise=None):
+def forward(dit_model, latent, caption_encoded, generator=None, t=None, noise=None, rope_starts_dev=None):
     """train.py:51-145 on the fused path.  latent [B,16,T,H,W], caption_encoded [B,512,4096] (bf16, CUDA).
     `t` / `noise` may be supplied (parity tests); otherwise drawn exactly like train.py:89-105."""
     device = latent.device
@@ -55,6 +55,78 @@ def forward(dit_model, latent, caption_encoded, generator=None, t=None, noise=No
     params = [p for _, p in dit_model.named_parameters()]
     need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     loss, loss_batchwise = TrainStepFunction.apply(dit_model, need, vae_latent, noise.contiguous(),
-                                                   caption_encoded.to(torch.bfloat16), t.to(torch.bfloat16), *params)
+                                                   caption_encoded.to(torch.bfloat16), t.to(torch.bfloat16), rope_starts_dev,
+                                                   *params)
     dit_model.last_loss_batchwise = loss_batchwise
     return loss, loss
+
+
+class GraphedTrainStep:
+    """One whole train step (zero_grad -> fused forward/loss -> backward -> FusedAdamW) captured in a CUDA graph.
+
+    Everything that changes from step to step lives in device buffers that are refreshed before each replay: the
+    batch, the RoPE start offsets (still drawn from the global CPU generator in the reference's order h, w, t) and the
+    optimizer scalars (per-group lr / wd, bias corrections).  World size 1 only (the per-block NCCL collectives of the
+    sharded path are issued from Python).  ~1100 kernel launches become one graph launch, which is what the small
+    workloads (DiT-B at 256x256, the S_small debug shape) are bound by.
+    """
+
+    def __init__(self, model, optimizer, latent_shape, context_shape, device="cuda", warmup=2):
+        from . import engine as _engine
+        assert model._flat is not None and model._flat.world == 1, "GraphedTrainStep: apply_fsdp(model) at world size 1"
+        self.model, self.opt, self._engine = model, optimizer, _engine
+        dev = torch.device(device)
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        self.latent = torch.zeros(latent_shape, **bf)
+        self.noise = torch.zeros(latent_shape, **bf)
+        self.context = torch.zeros(context_shape, **bf)
+        self.t = torch.zeros((latent_shape[0],), **bf)
+        self.starts_dev = torch.zeros(3, device=dev, dtype=torch.int32)
+        self.starts_host = torch.zeros(3, dtype=torch.int32).pin_memory()
+        self.hyper_dev = torch.zeros(34, device=dev, dtype=torch.float32)
+        self.hyper_host = torch.zeros(34, dtype=torch.float32).pin_memory()
+        B, C, T, H, W = latent_shape
+        self.thw = (T // model.time_patch_size, H // model.patch_size, W // model.patch_size)
+        self.graph = None
+        self.loss = None
+        self.warmup = warmup
+        self.calls = 0
+        self.launches_per_step = 0
+
+    def _refresh_scalars(self):
+        st, sh, sw = self._engine.draw_rope_starts(self.model.rope, self.thw)   # consumes the CPU RNG like the reference
+        self.starts_host[0], self.starts_host[1], self.starts_host[2] = st, sh, sw
+        self.starts_dev.copy_(self.starts_host, non_blocking=True)
+        self.hyper_host.copy_(torch.tensor(self.opt.hyper_values(self.opt._step + 1), dtype=torch.float32))
+        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
+
+    def _step_body(self):
+        self.opt.zero_grad()
+        loss, _ = forward(self.model, self.latent, self.context, t=self.t, noise=self.noise,
+                          rope_starts_dev=self.starts_dev)
+        loss.backward()
+        self.opt.step()
+        return loss
+
+    def __call__(self, latent, context, t, noise):
+        self.latent.copy_(latent, non_blocking=True)
+        self.context.copy_(context, non_blocking=True)
+        self.t.copy_(t, non_blocking=True)
+        self.noise.copy_(noise, non_blocking=True)
+        self._refresh_scalars()
+        self.opt.hyper_dev = self.hyper_dev
+        if self.graph is None:
+            if self.calls < self.warmup:            # eager warm-up steps (kernel attributes, allocator, NCCL-free path)
+                self.calls += 1
+                return self._step_body().detach()
+            from . import lib as _lib
+            self.graph = torch.cuda.CUDAGraph()
+            step_before = self.opt._step
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(self.graph):
+                self.loss = self._step_body().detach()
+            self.launches_per_step = _lib.launch_count() - n0   # kernels of ours inside one replay
+            self.opt._step = step_before              # capture does not execute; the replay below is the real step
+        self.graph.replay()
+        self.opt._step += 1
+        return self.loss
