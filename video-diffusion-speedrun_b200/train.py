@@ -92,6 +92,7 @@ class GraphedTrainStep:
         self.warmup = warmup
         self.calls = 0
         self.launches_per_step = 0
+        self._side = None
 
     def _refresh_scalars(self):
         st, sh, sw = self._engine.draw_rope_starts(self.model.rope, self.thw)   # consumes the CPU RNG like the reference
@@ -101,12 +102,19 @@ class GraphedTrainStep:
         self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
 
     def _step_body(self):
-        self.opt.zero_grad()
-        loss, _ = forward(self.model, self.latent, self.context, t=self.t, noise=self.noise,
-                          rope_starts_dev=self.starts_dev)
-        loss.backward()
-        self.opt.step()
-        return loss
+        """The step without torch.autograd in the loop (the engine's forward / backward are called directly), so the
+        capture contains only our kernels + memsets and no autograd-engine stream bookkeeping."""
+        model, eng = self.model, self._engine
+        with torch.no_grad():
+            self.opt.zero_grad()
+            P = model._param_view()
+            out, c = eng.forward(model, P, self.latent, self.context, self.t, save=True, noise=self.noise,
+                                 rope_starts_dev=self.starts_dev)
+            loss, d_out, lb = ops.loss_fwd_bwd(self.latent, self.noise, out, want_grad=True, want_batch=True)
+            model.last_loss_batchwise = lb
+            eng.run_backward(model, P, c, d_out, None)
+            self.opt.step()
+        return loss.view(())
 
     def __call__(self, latent, context, t, noise):
         self.latent.copy_(latent, non_blocking=True)
@@ -116,14 +124,23 @@ class GraphedTrainStep:
         self._refresh_scalars()
         self.opt.hyper_dev = self.hyper_dev
         if self.graph is None:
-            if self.calls < self.warmup:            # eager warm-up steps (kernel attributes, allocator, NCCL-free path)
+            # PyTorch's whole-network capture recipe: warm up on the side stream the capture will use (autograd's
+            # stream bookkeeping must not reference work on the caller's stream), then capture there.
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            if self.calls < self.warmup:
                 self.calls += 1
-                return self._step_body().detach()
+                with torch.cuda.stream(self._side):
+                    loss = self._step_body().detach()
+                cur.wait_stream(self._side)
+                return loss
             from . import lib as _lib
             self.graph = torch.cuda.CUDAGraph()
             step_before = self.opt._step
             n0 = _lib.launch_count()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=self._side):
                 self.loss = self._step_body().detach()
             self.launches_per_step = _lib.launch_count() - n0   # kernels of ours inside one replay
             self.opt._step = step_before              # capture does not execute; the replay below is the real step
