@@ -300,7 +300,7 @@ def run_ours(args):
             "step_frac_of_bf16_peak": step_flops / (step_ms * 1e-3) / 1e12 / peak,
             "roofline": {"kernel": "attn_bwd_kernel (self-attention backward, L=%d)" % Lr, "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": 123.7e6 if args.workload == "debug-8k" else None,
+                         "traffic": 127.4e6 if args.workload == "debug-8k" else None,
                          "traffic_note": "dram__bytes_read+write per launch, ncu --set full (profiles/r1_ncu_attention_full.md)",
                          "peak_source": pk_src + " (bf16_tflops_sustained)",
                          "kernel_ms": kern_ms, "launches_timed": len(prof),
