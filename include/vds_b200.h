@@ -139,7 +139,10 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
                  int64_t ldo, const void* d_o, int64_t lddo, const float* lse, float* delta, float* dq_acc,
                  int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, float* dk_acc, float* dv_acc,
                  int64_t ldkv_acc, int q_splits, int B, int nh, int Lq, int Lk, int head_dim, float scale,
-                 void* stream);
+                 void* tail_ws, int64_t tail_ws_bytes, void* stream);
+/* tail_ws (optional, q_splits == 1): fp32 workspace of vds_attn_bwd_tail_ws_bytes() bytes that lets the kernel split the
+ * items of the partly-filled last wave along the query range (tail balancing); contents need no initialisation. */
+int64_t vds_attn_bwd_tail_ws_bytes(int B, int nh, int Lk);
 
 /* tuning aid: per-iteration clock64 trace of one CTA of attn_bwd (NULL disables). */
 int vds_debug_attn_bwd_trace(void* buf);

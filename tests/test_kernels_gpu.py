@@ -239,7 +239,8 @@ def _ref_attn(q, k, v):
     return F.scaled_dot_product_attention(q.float(), k.float(), v.float())
 
 
-@pytest.mark.parametrize("B,nh,Lq,Lk", [(1, 1, 128, 128), (2, 4, 272, 272), (1, 2, 528, 512), (2, 4, 2064, 2064)])
+@pytest.mark.parametrize("B,nh,Lq,Lk", [(1, 1, 128, 128), (2, 4, 272, 272), (1, 2, 528, 512), (2, 4, 2064, 2064),
+                                        (3, 4, 2192, 2192)])   # 216 items on 148 SMs -> tail balancing path
 def test_attn_fwd_bwd(cuda_dev, B, nh, Lq, Lk):
     from vds_b200 import ops
     hd, h = 128, nh * 128

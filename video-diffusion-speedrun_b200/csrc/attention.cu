@@ -324,13 +324,15 @@ struct AttnBwdParams {
   bf16* dk; long long lddk;                // bf16 [B, Lk, lddk], head at head*128 (q_splits == 1)
   bf16* dv; long long lddv;
   float* dk_acc; float* dv_acc; long long ldkv_acc;  // fp32 accumulation targets when q_splits > 1
+  float* compact_acc;   // q_splits > 1: [item - item_base][dk|dv][128][128] fp32 (tail balancing), overrides dk_acc/dv_acc
+  int item_base, kv_tiles;
   int Lq, Lk, nh, q_splits;
   float scale_log2, scale;
   long long* dbg;   // optional per-iteration clock64 trace of CTA (0,0,0): [iter][8] (debug / tuning only)
 };
 #define VDS_TRACE(slot, it)                                                                      \
   do {                                                                                           \
-    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (it) < 160) \
+    if (p.dbg != nullptr && blockIdx.x == 0 && (it) < 160)                                       \
       p.dbg[(it) * 8 + (slot)] = clock64();                                                      \
   } while (0)
 
@@ -376,8 +378,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + BWD_OFF_BAR + 112);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv_tile = blockIdx.x / p.q_splits, split = blockIdx.x % p.q_splits;
-  const int head = blockIdx.y, b = blockIdx.z;
+  // 1-D grid over (item, split); item = (b * nh + head) * kv_tiles + kv_tile
+  const int item = p.item_base + blockIdx.x / p.q_splits, split = blockIdx.x % p.q_splits;
+  const int kv_tile = item % p.kv_tiles;
+  const int head = (item / p.kv_tiles) % p.nh, b = item / (p.kv_tiles * p.nh);
   const int kv0 = kv_tile * 128;
   const int n_q_all = (p.Lq + QSUB - 1) / QSUB;
   const int per = (n_q_all + p.q_splits - 1) / p.q_splits;
@@ -624,8 +628,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               *reinterpret_cast<uint4*>(dst + g * 8) = u;
             }
           } else {
-            float* dst = (which == 0 ? p.dk_acc : p.dv_acc) + ((long long)b * p.Lk + krow) * p.ldkv_acc +
-                         head * HD + c * 32;
+            float* dst = p.compact_acc != nullptr
+                             ? p.compact_acc + ((long long)(item - p.item_base) * 2 + which) * (128 * HD) + r * HD + c * 32
+                             : (which == 0 ? p.dk_acc : p.dv_acc) + ((long long)b * p.Lk + krow) * p.ldkv_acc +
+                                   head * HD + c * 32;
 #pragma unroll
             for (int g = 0; g < 8; ++g)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
@@ -643,6 +649,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 long long* g_attn_bwd_trace = nullptr;   // set through vds_debug_attn_bwd_trace (tuning only)
+
+// tail balancing fix-up: compact fp32 [item][dk|dv][128][128] -> bf16 dk / dv tiles
+__global__ void __launch_bounds__(256) attn_bwd_tail_fixup_kernel(const float* __restrict__ compact, bf16* __restrict__ dk,
+                                                                  long long lddk, bf16* __restrict__ dv, long long lddv,
+                                                                  int item_base, int kv_tiles, int nh, int Lk) {
+  const int item = item_base + blockIdx.x;
+  const int kv_tile = item % kv_tiles, head = (item / kv_tiles) % nh, b = item / (kv_tiles * nh);
+  const float* src = compact + (long long)blockIdx.x * 2 * 128 * HD;
+  for (int idx = threadIdx.x; idx < 2 * 128 * (HD / 8); idx += blockDim.x) {
+    const int which = idx / (128 * (HD / 8));
+    const int rem = idx % (128 * (HD / 8));
+    const int r = rem / (HD / 8), c8 = rem % (HD / 8);
+    const int krow = kv_tile * 128 + r;
+    if (krow >= Lk) continue;
+    const float4 a = *reinterpret_cast<const float4*>(src + (which * 128 + r) * HD + c8 * 8);
+    const float4 c = *reinterpret_cast<const float4*>(src + (which * 128 + r) * HD + c8 * 8 + 4);
+    uint4 u;
+    u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w); u.z = pack_bf16x2(c.x, c.y); u.w = pack_bf16x2(c.z, c.w);
+    bf16* dst = (which == 0 ? dk + ((long long)b * Lk + krow) * lddk : dv + ((long long)b * Lk + krow) * lddv) + head * HD + c8 * 8;
+    *reinterpret_cast<uint4*>(dst) = u;
+  }
+}
 
 static int make_tmap_tokens(CUtensorMap* tm, const void* ptr, long long ld, int L, int nh, int B, int box_rows = 128) {
   uint64_t dims[4] = {(uint64_t)HD, (uint64_t)L, (uint64_t)nh, (uint64_t)B};
@@ -696,13 +724,18 @@ int vds_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   return VDS_OK;
 }
 
+int64_t vds_attn_bwd_tail_ws_bytes(int B, int nh, int Lk) {
+  (void)B; (void)nh; (void)Lk;
+  return (int64_t)(num_sms() - 1) * 2 * 128 * HD * 4;   // at most SMs-1 remainder items
+}
+
 /* delta = rowsum(dO * O); dq_acc must be zero-initialised fp32 [B, Lq, lddq]; with q_splits > 1 dk/dv are
  * accumulated into zero-initialised fp32 buffers dk_acc/dv_acc [B, Lk, ldkv_acc] instead of dk/dv. */
 int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
                  int64_t ldo, const void* d_o, int64_t lddo, const float* lse, float* delta, float* dq_acc,
                  int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, float* dk_acc, float* dv_acc,
                  int64_t ldkv_acc, int q_splits, int B, int nh, int Lq, int Lk, int head_dim, float scale,
-                 void* stream) {
+                 void* tail_ws, int64_t tail_ws_bytes, void* stream) {
   VDS_CHECK_ARG(head_dim == HD, "attn_bwd: head_dim=%d unsupported (only 128)", head_dim);
   VDS_CHECK_ARG(q_splits >= 1, "attn_bwd: q_splits");
   VDS_CHECK_ARG(q_splits == 1 ? (dk && dv) : (dk_acc && dv_acc), "attn_bwd: missing dk/dv target");
@@ -733,8 +766,37 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   p.Lq = Lq; p.Lk = Lk; p.nh = nh; p.q_splits = q_splits;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.dbg = g_attn_bwd_trace;
-  dim3 grid(((Lk + 127) / 128) * q_splits, nh, B);
-  attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, tdo, tdq, p);
+  p.compact_acc = nullptr;
+  const int kv_tiles = (Lk + 127) / 128;
+  p.kv_tiles = kv_tiles;
+  const int total = kv_tiles * nh * B;
+  // Tail balancing: with one CTA per (kv tile, head, batch) the last wave of the grid is partly empty (520 items on 148
+  // SMs = 3.51 waves cost 4).  The remainder items are split `s` ways along the query range in a second launch (fp32
+  // red into a compact workspace + a bf16 fix-up), so the tail costs ceil(rem*s/SMs)/s waves instead of 1.
+  int tail_s = 0;
+  const int sms = num_sms();
+  const int full = (total / sms) * sms, rem = total - full;
+  if (q_splits == 1 && tail_ws != nullptr && full > 0 && rem > 0 && (Lq + QSUB - 1) / QSUB >= 32) {
+    double best = 1.0;
+    for (int s = 2; s <= 8; ++s) {
+      const double cost = (double)((rem * s + sms - 1) / sms) / s + 0.02 * s;   // + per-split prologue / atomics
+      if (cost < best - 0.1 && (long long)rem * 2 * 128 * HD * 4 <= tail_ws_bytes) { best = cost; tail_s = s; }
+    }
+  }
+  if (tail_s == 0) {
+    p.item_base = 0;
+    attn_bwd_kernel<<<total * q_splits, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, tdo, tdq, p);
+  } else {
+    p.item_base = 0;
+    attn_bwd_kernel<<<full, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, tdo, tdq, p);
+    VDS_CHECK_LAUNCH("attn_bwd");
+    cudaMemsetAsync(tail_ws, 0, (size_t)rem * 2 * 128 * HD * 4, (cudaStream_t)stream);
+    p.item_base = full; p.q_splits = tail_s; p.compact_acc = (float*)tail_ws;
+    attn_bwd_kernel<<<rem * tail_s, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, tdo, tdq, p);
+    VDS_CHECK_LAUNCH("attn_bwd");
+    attn_bwd_tail_fixup_kernel<<<rem, 256, 0, (cudaStream_t)stream>>>((const float*)tail_ws, (bf16*)dk, lddk, (bf16*)dv,
+                                                                      lddv, full, kv_tiles, nh, Lk);
+  }
   VDS_CHECK_LAUNCH("attn_bwd");
   return VDS_OK;
 }

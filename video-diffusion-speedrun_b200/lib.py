@@ -66,7 +66,7 @@ _SIGNATURES = {
     "vds_accum_bf16_f32": [vp, vp, i64, i32, vp],
     "vds_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, f32, vp],
     "vds_attn_bwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp, i64, vp, vp,
-                     i64, i32, i32, i32, i32, i32, i32, f32, vp],
+                     i64, i32, i32, i32, i32, i32, i32, f32, vp, i64, vp],
     "vds_debug_attn_bwd_trace": [vp],
     "vds_debug_gemm2_trace": [vp],
     "vds_loss_fwd_bwd": [vp, vp, vp, vp, vp, vp, i32, i64, f32, vp, vp],
@@ -87,6 +87,8 @@ def lib():
         L.vds_last_error.restype = ctypes.c_char_p
         L.vds_abi_version.restype = ctypes.c_int
         L.vds_launch_count.restype = ctypes.c_int64
+        L.vds_attn_bwd_tail_ws_bytes.restype = ctypes.c_int64
+        L.vds_attn_bwd_tail_ws_bytes.argtypes = [i32, i32, i32]
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = argtypes

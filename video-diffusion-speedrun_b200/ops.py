@@ -251,11 +251,23 @@ def attn_fwd(q, k, v, B, nh, Lq, Lk, out=None, want_lse=True, hd=128):
     return out, lse
 
 
+_TAIL_WS = {}
+
+
+def _tail_ws(device, B, nh, Lk):
+    ws = _TAIL_WS.get(device)
+    if ws is None:
+        ws = torch.empty(int(L.lib().vds_attn_bwd_tail_ws_bytes(B, nh, Lk)), device=device, dtype=torch.uint8)
+        _TAIL_WS[device] = ws
+    return ws
+
+
 def attn_bwd(q, k, v, o, d_o, lse, B, nh, Lq, Lk, dq_acc, dk=None, dv=None, dk_acc=None, dv_acc=None, q_splits=1,
-             hd=128):
+             hd=128, tail_balance=True):
     """dq_acc: zeroed fp32 [B*Lq, nh*hd]; dk/dv: bf16 2-D views (q_splits == 1) or fp32 accumulators."""
     _chk_bf16(q, k, v, o, d_o)
     delta = torch.empty((B, nh, Lq), device=q.device, dtype=torch.float32)
+    ws = _tail_ws(q.device, B, nh, Lk) if (tail_balance and q_splits == 1) else None
     prof = PROFILE.get("attn_bwd_self") if Lq == Lk else None
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -264,7 +276,8 @@ def attn_bwd(q, k, v, o, d_o, lse, B, nh, Lq, Lk, dq_acc, dk=None, dv=None, dk_a
         _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(d_o), d_o.stride(0),
         _p(lse), _p(delta), _p(dq_acc), dq_acc.stride(0), _p(dk), dk.stride(0) if dk is not None else 0, _p(dv),
         dv.stride(0) if dv is not None else 0, _p(dk_acc), _p(dv_acc),
-        dk_acc.stride(0) if dk_acc is not None else 0, q_splits, B, nh, Lq, Lk, hd, float(hd) ** -0.5, _s()),
+        dk_acc.stride(0) if dk_acc is not None else 0, q_splits, B, nh, Lq, Lk, hd, float(hd) ** -0.5,
+        _p(ws), ws.numel() if ws is not None else 0, _s()),
         "vds_attn_bwd")
     if prof is not None:
         e1.record()
