@@ -17,12 +17,12 @@ torch.cuda.synchronize()
 lib.lib().vds_debug_attn_bwd_trace(None)
 t = tr.cpu()
 t0 = t[0, 0].item()
-names = ["sdp_issue", "mma_issue", "cmp_start", "math_done", "pds_arrive", "drain_start", "drained"]
+names = ["sdp_issue", "mma_issue", "cmp_start", "math_done", "pds_arrive", "drain_start", "drained", "s_issued"]
 print("iter " + " ".join(f"{n:>11s}" for n in names))
-for i in list(range(0, 6)) + list(range(60, 66)):
-    print(f"{i:4d} " + " ".join(f"{(t[i, s].item() - t0):11d}" for s in range(7)))
-d = t[20:120]
-print("mean period (cycles):", (d[-1, 1] - d[0, 1]).item() / 99)
+for i in list(range(0, 6)) + list(range(30, 36)):
+    print(f"{i:4d} " + " ".join(f"{(t[i, s].item() - t0):11d}" for s in range(8)))
+d = t[10:50]
+print("mean period (cycles):", (d[-1, 1] - d[0, 1]).item() / 39)
 print("compute: start->math_done", (d[:, 3] - d[:, 2]).float().mean().item(), " math_done->pds", (d[:, 4] - d[:, 3]).float().mean().item())
 print("mma_issue(i) - pds_arrive(i)", (d[:, 1] - d[:, 4]).float().mean().item())
 print("drain_start(i) - mma_issue(i)", (d[:, 5] - d[:, 1]).float().mean().item(), " drained - drain_start", (d[:, 6] - d[:, 5]).float().mean().item())

@@ -336,13 +336,17 @@ struct AttnBwdParams {
       p.dbg[(it) * 8 + (slot)] = clock64();                                                      \
   } while (0)
 
-// Backward v1.  CTA = one 128-row K/V tile of one (b, head), looping over 64-row query sub-tiles:
-//   S^T = K Q^T, dP^T = V dO^T          (TMEM, double-buffered)        M=128 (kv) N=64 (q)  K=128 (d)
-//   P^T, dS^T -> bf16 smem (SW128)      (compute warpgroup, thread == kv row)
+// Backward.  CTA = one 128-row K/V tile of one (b, head), looping over 64-row query sub-tiles:
+//   S^T = K Q^T (double-buffered), dP^T = V dO^T (single buffer)   TMEM   M=128 (kv) N=64 (q)  K=128 (d)
+//   P^T, dS^T -> bf16 into the retired S^T columns (A operands of dV / dK); dS^T also -> smem (B operand of dQ^T)
 //   dV += P^T dO, dK += dS^T Q          (TMEM accumulators)            M=128 (kv) N=128 (d) K=64 (q)
-//   dQ^T = K^T dS^T                     (TMEM, aliases the S^T buffer) M=128 (d)  N=64 (q)  K=128 (kv)
+//   dQ^T = K^T dS^T                     (TMEM, own 64 columns)         M=128 (d)  N=64 (q)  K=128 (kv)
 //   dQ^T -> fp32 smem tile [q][d] -> cp.reduce.async.bulk.tensor (TMA adds it into the fp32 dq buffer)
 // warp 0 TMA producer (K,V once; Q/dO ring of 3) | warp 1 MMA issuer | warps 4-7 compute | warps 8-11 dQ drain.
+// Measured (scripts/mma_shapes.cu, scripts/bwd_trace.py): tcgen05.mma issue blocks on a shallow queue, an SS-mode
+// M128 N64 K16 MMA costs 53 cycles (6 KiB of operand reads at 128 B/clk) against 37 with A in TMEM, and the loop moves
+// ~288 KiB of shared-memory traffic per sub-tile (operands 176, Q/dO fill 32, dS^T 16, dQ staging 2 x 32): the kernel
+// runs at ~90% of the shared-memory port, which is what bounds it.
 constexpr int BWD_THREADS = 384;
 constexpr int QSUB = 64;
 constexpr int QT_BYTES = QSUB * HD * 2;          // 16 KiB: 64 x 128 bf16 (two [64 x 128 B] halves)
@@ -374,7 +378,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t bars = base + BWD_OFF_BAR;
   const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 32, sdp_full = bars + 56,
                  pds_full = bars + 72, mma_done = bars + 80, dq_drained = bars + 96, tmem_slot = bars + 112,
-                 stat_full = bars + 120;
+                 stat_full = bars + 120, dp_full = bars + 136, dp_read = bars + 144, dq_full = bars + 152;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + BWD_OFF_BAR + 112);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -398,6 +402,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(stat_full + 8 * s, 128);
     }
     mbar_init(pds_full, 128);
+    mbar_init(dp_full, 1);
+    mbar_init(dp_read, 128);
+    mbar_init(dq_full, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmDQ);
@@ -407,8 +414,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_gen;
-  const uint32_t tDV = tmem, tDK = tmem + 128;
-  // buffer bb: S^T at 256 + bb*128 (64 cols, later reused for dQ^T), dP^T right behind it (64 cols)
+  // TMEM columns: dV [0,128) | dK [128,256) | S^T buffer 0 / 1 [256,320) / [320,384) (afterwards bf16 P^T in its
+  // columns 0..31 and dS^T in 32..63: the A operands of dV / dK) | dP^T [384,448) | dQ^T [448,512)
+  const uint32_t tDV = tmem, tDK = tmem + 128, tSTb = tmem + 256, tDPTs = tmem + 384, tDQT = tmem + 448;
 
   if (n_q > 0) {
     if (warp == 0) {
@@ -435,53 +443,72 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, false, false);     // S^T, dP^T
       constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, false, true);   // dV, dK
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, true, true);      // dQ^T
-      auto issue_sdp = [&](int k) {
+      // tcgen05.mma issue blocks while the (shallow) tensor queue is full, so this warp's program order IS the tensor
+      // pipe's schedule.  Per sub-tile i:  S^T(i+1) | dP^T(i+1) | dQ^T(i) | dV(i), dK(i).  The first two only wait for
+      // buffers the compute warps released long ago, so the pipe keeps running while sub-tile i is in the softmax math.
+      auto issue_s = [&](int k) {
         const int bb = k & 1, st = k % 3;
         mbar_wait(qdo_full + 8 * st, (k / 3) & 1);
-        if (k >= 2) mbar_wait(dq_drained + 8 * bb, ((k >> 1) - 1) & 1);
         mbar_wait(stat_full + 8 * bb, (k >> 1) & 1);
         tc_fence_after();
         if (elect_one()) {
-          VDS_TRACE(0, k);   // S/dP(k) issue
-          const uint32_t q = sQ + st * 2 * QT_BYTES, d_o = q + QT_BYTES;
-          const uint32_t tST = tmem + 256 + bb * 128, tDPT = tST + 64;
+          VDS_TRACE(0, k);   // S(k) issue
+          const uint32_t q = sQ + st * 2 * QT_BYTES;
+          const uint32_t tST = tSTb + bb * 64;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // S^T = K Q^T : B = Q tile, K-major, 64 rows per half
+          for (int kk = 0; kk < 8; ++kk)
             umma_bf16(tST, desc_kmajor(sK, kk), umma_smem_desc(q + (kk >> 2) * QT_HALF + (kk & 3) * 32, 16, 1024),
                       idesc_s, kk > 0);
           umma_bf16(tST, desc_k16_noswz(sPT), desc_k16_noswz(sPT + 4096 + (bb * 2 + 0) * 2048), idesc_s, 1);  // - lse
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dP^T = V dO^T
-            umma_bf16(tDPT, desc_kmajor(sV, kk), umma_smem_desc(d_o + (kk >> 2) * QT_HALF + (kk & 3) * 32, 16, 1024),
-                      idesc_s, kk > 0);
-          umma_bf16(tDPT, desc_k16_noswz(sPT), desc_k16_noswz(sPT + 4096 + (bb * 2 + 1) * 2048), idesc_s, 1);  // - delta
           umma_commit(sdp_full + 8 * bb);
+          VDS_TRACE(7, k);   // S(k) issued
+        }
+        __syncwarp();
+      };
+      // dP^T(k) = V dO^T into the single dP^T buffer (free once dp_read says the compute warps hold dP^T(k-1) in registers)
+      auto issue_dp = [&](int k) {
+        const int bb = k & 1, st = k % 3;
+        if (k > 0) mbar_wait(dp_read, (k - 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d_o = sQ + st * 2 * QT_BYTES + QT_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16(tDPTs, desc_kmajor(sV, kk), umma_smem_desc(d_o + (kk >> 2) * QT_HALF + (kk & 3) * 32, 16, 1024),
+                      idesc_s, kk > 0);
+          umma_bf16(tDPTs, desc_k16_noswz(sPT), desc_k16_noswz(sPT + 4096 + (bb * 2 + 1) * 2048), idesc_s, 1);  // - delta
+          umma_commit(dp_full);
         }
         __syncwarp();
       };
       mbar_wait(kv_full, 0);
-      issue_sdp(0);
+      issue_s(0);
+      issue_dp(0);
       for (int i = 0; i < n_q; ++i) {
         const int bb = i & 1, st = i % 3;
-        if (i + 1 < n_q) issue_sdp(i + 1);
+        if (i + 1 < n_q) {
+          issue_s(i + 1);
+          issue_dp(i + 1);
+        }
         mbar_wait(pds_full, i & 1);
+        if (i > 0) mbar_wait(dq_drained, (i - 1) & 1);
         tc_fence_after();
         if (elect_one()) {
-          VDS_TRACE(1, i);   // dV/dK/dQ(i) issue
+          VDS_TRACE(1, i);   // dQ/dV/dK(i) issue
           const uint32_t q = sQ + st * 2 * QT_BYTES, d_o = q + QT_BYTES;
-          const uint32_t tPT = tmem + 256 + bb * 128, tDSTm = tPT + 64;   // bf16 P^T / dS^T in the retired S^T / dP^T columns
+          const uint32_t tPT = tSTb + bb * 64;   // bf16 P^T (columns 0..31) and dS^T (32..63) in the retired S^T columns
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)   // dQ^T = K^T dS^T : A = K MN-major (M = d), B = dS^T MN-major (N = q)
+            umma_bf16(tDQT, desc_mnmajor(sK, kk), umma_smem_desc(sDST + kk * 2048, 16, 1024), idesc_dq, kk > 0);
+          umma_commit(dq_full);            // first: the drain warpgroup starts early and the dS^T smem tile is free again
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)   // dV += P^T dO : A = P^T (TMEM, 8 columns per k-step), B = dO MN-major (N = d)
             umma_bf16_ts(tDV, tPT + kk * 8, umma_smem_desc(d_o + kk * 2048, QT_HALF, 1024), idesc_acc,
                          (i > 0 || kk > 0));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)   // dK += dS^T Q : A = dS^T (TMEM)
-            umma_bf16_ts(tDK, tDSTm + kk * 8, umma_smem_desc(q + kk * 2048, QT_HALF, 1024), idesc_acc,
+            umma_bf16_ts(tDK, tPT + 32 + kk * 8, umma_smem_desc(q + kk * 2048, QT_HALF, 1024), idesc_acc,
                          (i > 0 || kk > 0));
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)   // dQ^T = K^T dS^T : A = K MN-major (M = d), B = dS^T MN-major (N = q)
-            umma_bf16(tmem + 256 + bb * 128, desc_mnmajor(sK, kk), umma_smem_desc(sDST + kk * 2048, 16, 1024),
-                      idesc_dq, kk > 0);
           umma_commit(qdo_empty + 8 * st);
           umma_commit(mma_done + 8 * bb);
         }
@@ -499,15 +526,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int sc = ct & 63;
       const float inv_sl2 = 1.0f / p.scale_log2;
       // value this thread contributes to the statistics tile of sub-tile k: -lse/scale_log2 (ct < 64) or -delta
-      auto stat_value = [&](int k) -> float {
+      // The global load is issued an iteration ahead as a bare ld (no dependent instruction until stat_finish at the
+      // end of the iteration), so its latency never stalls this warp.
+      auto stat_fetch = [&](int k) -> float {
+        const int q = min((qt0 + k) * QSUB + sc, p.Lq - 1);
+        float raw;
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(raw) : "l"(stat_src + q));
+        return raw;
+      };
+      auto stat_finish = [&](int k, float raw) -> float {
         const int q = (qt0 + k) * QSUB + sc;
         if (q >= p.Lq) return ct < 64 ? -INFINITY : 0.f;        // padded query row: exp2(-inf) = 0
-        return ct < 64 ? -stat_src[q] * inv_sl2 : -stat_src[q];
+        return ct < 64 ? -raw * inv_sl2 : -raw;
       };
-      auto stat_store = [&](int k, float v) {
+      auto stat_value = [&](int k) -> float { return stat_finish(k, stat_fetch(k)); };
+      auto stat_write = [&](int k, float v) {
         uint8_t* tile = gPT + 4096 + ((k & 1) * 2 + (ct < 64 ? 0 : 1)) * 2048;
         *reinterpret_cast<uint4*>(tile + k16_off(sc)) = split3_bf16(v);
         *reinterpret_cast<uint4*>(tile + k16_off(sc) + 128) = make_uint4(0u, 0u, 0u, 0u);
+      };
+      auto stat_store = [&](int k, float v) {
+        stat_write(k, v);
         fence_proxy_async_smem();
         mbar_arrive(stat_full + 8 * (k & 1));
       };
@@ -521,49 +560,72 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool kv_full_tile = kv0 + 128 <= p.Lk;
       for (int i = 0; i < n_q; ++i) {
         const int bb = i & 1;
-        const float next_stat = (i + 2 < n_q) ? stat_value(i + 2) : 0.f;   // prefetched; stored at the end of this iteration
+        const float next_raw = (i + 2 < n_q) ? stat_fetch(i + 2) : 0.f;   // prefetched; stored at the end of this iteration
         mbar_wait(sdp_full + 8 * bb, (i >> 1) & 1);
         tc_fence_after();
-        if (ct == 0) VDS_TRACE(2, i);   // compute sees S/dP(i)
-        const uint32_t tST = tmem + 256 + bb * 128 + lane_off, tDPT = tST + 64;
-        uint32_t pp[32], dd[32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t sv[32], dv[32];
-          tmem_ld32(tST + c * 32, sv);
-          tmem_ld32(tDPT + c * 32, dv);
+        if (ct == 0) VDS_TRACE(2, i);   // compute sees S(i)
+        const uint32_t tST = tSTb + bb * 64 + lane_off, tDPT = tDPTs + lane_off;
+        // phase 1 (overlaps the dV/dK/dQ MMAs of the previous sub-tile): p = exp2(s'), P^T -> TMEM
+        float pf[64];
+        {
+          uint32_t sv0[32], sv1[32];
+          tmem_ld32(tST, sv0);
+          tmem_ld32(tST + 32, sv1);
           tmem_ld_wait();
-          // S^T already carries -lse (and dP^T carries -delta) from the statistics k-step of the MMA
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            float p0 = ex2(__uint_as_float(sv[e]) * p.scale_log2);
-            float p1 = ex2(__uint_as_float(sv[e + 1]) * p.scale_log2);
+          for (int e = 0; e < 32; ++e) {
+            float p0 = ex2(__uint_as_float(sv0[e]) * p.scale_log2);
+            float p1 = ex2(__uint_as_float(sv1[e]) * p.scale_log2);
             if (!kv_full_tile) {
               p0 = kv_ok ? p0 : 0.f;
               p1 = kv_ok ? p1 : 0.f;
             }
-            const float d0 = p0 * (__uint_as_float(dv[e]) * p.scale);
-            const float d1 = p1 * (__uint_as_float(dv[e + 1]) * p.scale);
-            pp[c * 16 + (e >> 1)] = pack_bf16x2(p0, p1);
+            pf[e] = p0;
+            pf[32 + e] = p1;
+          }
+        }
+        {
+          uint32_t pp[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) pp[e] = pack_bf16x2(pf[2 * e], pf[2 * e + 1]);
+          tmem_st32(tST, pp);
+        }
+        // phase 2: dS^T = P^T o dP'^T * scale once dP^T(i) has landed
+        mbar_wait(dp_full, i & 1);
+        tc_fence_after();
+        uint32_t dd[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t dv[32];
+          tmem_ld32(tDPT + c * 32, dv);
+          tmem_ld_wait();
+          if (c == 1) {   // dP^T(i) is in registers: the MMA warp may refill the buffer with dP^T(i+1)
+            tc_fence_before();
+            mbar_arrive(dp_read);
+          }
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float d0 = pf[c * 32 + e] * (__uint_as_float(dv[e]) * p.scale);
+            const float d1 = pf[c * 32 + e + 1] * (__uint_as_float(dv[e + 1]) * p.scale);
             dd[c * 16 + (e >> 1)] = pack_bf16x2(d0, d1);
           }
         }
-        // P^T and dS^T become TMEM-resident A operands (they overwrite the S^T / dP^T columns this thread just
-        // read); dS^T additionally goes to shared memory as the B operand of dQ^T = K^T dS^T.
-        tmem_st32(tST, pp);
-        tmem_st32(tDPT, dd);
+        tmem_st32(tST + 32, dd);
         if (ct == 0) VDS_TRACE(3, i);   // math done
-        if (i > 0) mbar_wait(mma_done + 8 * (bb ^ 1), ((i - 1) >> 1) & 1);   // dS^T smem tile consumed by dQ^T(i-1)
+        if (i > 0) mbar_wait(dq_full, (i - 1) & 1);   // dS^T smem tile consumed by dQ^T(i-1)
+        uint8_t* gDSTb = gDST;
 #pragma unroll
         for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<uint4*>(gDST + sw128_offset(r, g)) =
+          *reinterpret_cast<uint4*>(gDSTb + sw128_offset(r, g)) =
               make_uint4(dd[g * 4], dd[g * 4 + 1], dd[g * 4 + 2], dd[g * 4 + 3]);
+        // statistics tile of sub-tile i+2 (buffer bb: S^T(i) and dP^T(i), its readers, are complete) shares the fence
+        if (i + 2 < n_q) stat_write(i + 2, stat_finish(i + 2, next_raw));
         tmem_st_wait();
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(pds_full);
-        if (ct == 0) VDS_TRACE(4, i);   // pds arrive
-        if (i + 2 < n_q) stat_store(i + 2, next_stat);   // buffer bb: its MMAs (S^T / dP^T of sub-tile i) are complete
+        if (i + 2 < n_q) mbar_arrive(stat_full + 8 * bb);
+        if (ct == 0) VDS_TRACE(4, i);   // pds arrive   // buffer bb: its MMAs (S^T / dP^T of sub-tile i) are complete
       }
     } else if (warp >= 8) {
       // ------------------------------------------------------------ dQ drain warpgroup (thread == d)
@@ -573,15 +635,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool leader = threadIdx.x == 256;
       for (int i = 0; i < n_q; ++i) {
         const int bb = i & 1;
-        mbar_wait(mma_done + 8 * bb, (i >> 1) & 1);
+        mbar_wait(dq_full, i & 1);
         tc_fence_after();
         if (leader) VDS_TRACE(5, i);   // drain sees dQ(i)
         uint32_t v0[32], v1[32];
-        tmem_ld32(tmem + 256 + bb * 128 + lane_off, v0);
-        tmem_ld32(tmem + 256 + bb * 128 + lane_off + 32, v1);
+        tmem_ld32(tDQT + lane_off, v0);
+        tmem_ld32(tDQT + lane_off + 32, v1);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(dq_drained + 8 * bb);
+        mbar_arrive(dq_drained);
         if (leader) VDS_TRACE(6, i);   // dq_drained arrive
         if (leader) bulk_wait_group_read0();      // previous reduction has finished reading the staging tile
         named_bar_sync(2, 128);
