@@ -104,3 +104,48 @@ def test_oracle_against_live_reference_if_present():
     P = {k: v for k, v in sd.items()}
     o_out = O.dit_forward(P, cfg, latent * (1 - tr) + noise * tr, context, t)
     assert (out - o_out).abs().max().item() < 1e-5
+
+
+def test_gelu_logistic_fit():
+    """The CUDA epilogues evaluate Phi(x) as 1 / (1 + 2^(x q(x^2))) (csrc/gemm_epilogue.cuh).  Re-evaluate exactly that
+    recipe in numpy float32 with the coefficients parsed from the header and compare with the erf definition the
+    reference uses (model.py:84-85, nn.GELU() = exact erf): the error must stay far below bf16 resolution."""
+    import re
+    import numpy as np
+    from scipy.special import erf
+
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "video-diffusion-speedrun_b200", "csrc",
+                            "gemm_epilogue.cuh")).read()
+    coef = {m.group(1): np.float32(m.group(2)) for m in re.finditer(r"#define VDS_GELU_([QW]\d) (\S+?)f\n", hdr)}
+    assert sorted(coef) == ["Q0", "Q1", "Q2", "Q3", "Q4", "W0", "W1", "W2", "W3", "W4"]
+    f = np.float32
+    x = np.linspace(-12, 12, 240001).astype(f)
+    x64 = x.astype(np.float64)
+    phi_ref = 0.5 * (1 + erf(x64 / np.sqrt(2)))
+    gelu_ref = x64 * phi_ref
+    dgelu_ref = phi_ref + x64 * np.exp(-x64 * x64 / 2) / np.sqrt(2 * np.pi)
+
+    def horner(prefix, s):
+        p = coef[prefix + "4"]
+        for k in (3, 2, 1, 0):
+            p = (p * s + coef[prefix + str(k)]).astype(f)
+        return p
+
+    def phi(s):
+        t = (x * horner("Q", s)).astype(f)
+        with np.errstate(over="ignore"):
+            e = np.exp2(t.astype(np.float64)).astype(f)
+        return (f(1) / (f(1) + e)).astype(f)
+
+    s = (x * x).astype(f)
+    g = (x * phi(s)).astype(f)
+    assert np.abs(g - gelu_ref).max() < 5e-6
+    sc = np.minimum(s, f(64))
+    r = phi(sc)
+    dg = ((x * horner("W", sc)) * (r * (f(1) - r)) + r).astype(f)
+    assert np.abs(dg - dgelu_ref).max() < 2e-5
+    # W_k are the derivative coefficients of the same polynomial: W_k = -(2k + 1) Q_k / log2(e)
+    for k in range(5):
+        assert abs(float(coef[f"W{k}"]) + (2 * k + 1) * float(coef[f"Q{k}"]) / 1.4426950408889634) < 1e-6 * (1 + abs(float(coef[f"W{k}"])))
+    # saturating tails: exactly 0 / x
+    assert g[0] == 0 and g[-1] == x[-1]

@@ -61,6 +61,7 @@ struct AdamArgs {
   const long long* chunk_start; const int* chunk_len; const int* chunk_group;
   float lr[16]; float wd[16];
   float beta1, beta2, eps, bc1, bc2_sqrt, gscale;
+  int vec_ok;               // all flat buffers 16-byte aligned (bf16 copy 8-byte)
   const float* hyper_dev;   // optional [lr[16] | wd[16] | bc1 | bc2_sqrt] in device memory (CUDA-graph replays)
 };
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a) {
@@ -73,16 +74,47 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a) {
     lr = a.hyper_dev[grp]; wd = a.hyper_dev[16 + grp]; bc1 = a.hyper_dev[32]; bc2_sqrt = a.hyper_dev[33];
   }
   const float decay = 1.0f - lr * wd, step = lr / bc1;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const long long k = s + i;
-    const float g = a.g[k] * a.gscale;
-    float p = a.p[k] * decay;
-    const float m = a.beta1 * a.m[k] + (1.0f - a.beta1) * g;
-    const float v = a.beta2 * a.v[k] + (1.0f - a.beta2) * g * g;
+  auto update = [&](float g, float& p, float& m, float& v) {
+    g *= a.gscale;
+    p *= decay;
+    m = a.beta1 * m + (1.0f - a.beta1) * g;
+    v = a.beta2 * v + (1.0f - a.beta2) * g * g;
     p -= step * m / (sqrtf(v) / bc2_sqrt + a.eps);
+  };
+  auto scalar = [&](long long k) {
+    float p = a.p[k], m = a.m[k], v = a.v[k];
+    update(a.g[k], p, m, v);
     a.p[k] = p; a.m[k] = m; a.v[k] = v;
     if (a.p_bf16 != nullptr) a.p_bf16[k] = __float2bfloat16_rn(p);
+  };
+  // 16-byte body (the flat buffers are 16-byte aligned; a chunk may start anywhere) with scalar head / tail
+  const int lead = a.vec_ok ? min(n, (int)((4 - (s & 3)) & 3)) : n;
+  const int nvec = (n - lead) >> 2;
+  if ((int)threadIdx.x < lead) scalar(s + threadIdx.x);
+  const long long vb = s + lead;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const long long k = vb + 4LL * i;
+    const float4 g4 = __ldcs(reinterpret_cast<const float4*>(a.g + k));
+    float4 p4 = *reinterpret_cast<const float4*>(a.p + k);
+    float4 m4 = *reinterpret_cast<const float4*>(a.m + k);
+    float4 v4 = *reinterpret_cast<const float4*>(a.v + k);
+    update(g4.x, p4.x, m4.x, v4.x);
+    update(g4.y, p4.y, m4.y, v4.y);
+    update(g4.z, p4.z, m4.z, v4.z);
+    update(g4.w, p4.w, m4.w, v4.w);
+    *reinterpret_cast<float4*>(a.p + k) = p4;
+    *reinterpret_cast<float4*>(a.m + k) = m4;
+    *reinterpret_cast<float4*>(a.v + k) = v4;
+    if (a.p_bf16 != nullptr) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(p4.x, p4.y), hi = __floats2bfloat162_rn(p4.z, p4.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(a.p_bf16 + k) = u;
+    }
   }
+  const int done = lead + 4 * nvec;
+  if ((int)threadIdx.x < n - done) scalar(s + done + threadIdx.x);
 }
 
 }  // namespace vds
@@ -123,6 +155,7 @@ int vds_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const 
   a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   a.gscale = grad_scale;
   a.hyper_dev = hyper_dev;
+  a.vec_ok = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)p_bf16 & 7) == 0;
   adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(a);
   VDS_CHECK_LAUNCH("adamw");
   return VDS_OK;

@@ -216,11 +216,22 @@ class GradSink:
             ops.colsum(dy, self.buf(name))
 
 
-def _attn_q_splits(n_kv_tiles, B, nh, n_q_tiles):
+def _attn_q_splits(n_kv_tiles, B, nh, n_q_tiles, sms=148):
+    """Query-range splits for an attention backward with fewer (kv tile, head, batch) items than SMs.
+
+    Cost model in units of one 64-row query sub-tile iteration: waves x (sub-tiles per CTA + fixed prologue /
+    epilogue of about 5 iterations: K/V fill, TMEM alloc, fp32 red of dK/dV)."""
     ctas = n_kv_tiles * B * nh
-    if ctas >= 148:
+    if ctas >= sms:
         return 1
-    return max(1, min(n_q_tiles, (2 * 148 + ctas - 1) // ctas))
+    n_sub = 2 * n_q_tiles
+    best, best_cost = 1, None
+    for qs in range(1, min(n_sub, 64) + 1):
+        waves = (ctas * qs + sms - 1) // sms
+        cost = waves * ((n_sub + qs - 1) // qs + 5)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = qs, cost
+    return best
 
 
 def backward(model, P, c, dout, sink):
