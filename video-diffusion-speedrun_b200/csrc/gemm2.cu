@@ -24,9 +24,18 @@ constexpr int G2_BN = 256;              // tile N of the CTA pair
 constexpr int G2_A_BYTES = BM * BK * 2;           // 16 KiB
 constexpr int G2_B_BYTES = (G2_BN / 2) * BK * 2;  // 16 KiB: this CTA's half of B
 constexpr int G2_STAGE = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_STAGES = 6;
-constexpr int G2_STG = 8 * 4096;
-constexpr int G2_SMEM = G2_STAGES * G2_STAGE + G2_STG + 256 + 1024;   // [stages][staging 8 x 4 KiB][barriers]
+constexpr int G2_MAX_STAGES = 6;
+// Shared memory: [stages x 32 KiB][8 epilogue warps x staging][barriers].  The plain / fp32 epilogues use 6 stages and
+// one 4 KiB staging tile per warp; the fused element-wise epilogues (GELU, gate+residual, dGELU) are bound by their
+// own latency chain, not by the operand pipeline, and trade one stage for a second staging tile per warp (aux
+// operand prefetched by TMA one group ahead / both outputs stored without waiting in between).
+template <int EPI>
+struct G2Cfg {
+  static constexpr bool fused = EPI == VDS_EPI_BIAS_GELU || EPI == VDS_EPI_GATE_RES || EPI == VDS_EPI_DGELU;
+  static constexpr int stages = fused ? 5 : 6;
+  static constexpr int stg_warp = fused ? 8192 : 4096;
+};
+constexpr int G2_SMEM = 6 * G2_STAGE + 8 * 4096 + 256 + 1024;   // same total for every variant
 // shared::cluster address of the same smem offset in CTA `rank` of this cluster
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t cta_addr, uint32_t rank) {
   uint32_t r;
@@ -70,23 +79,180 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
+
+// Fused element-wise epilogue of one warp (32 accumulator rows x its 128-column half of the tile, as two 64-column
+// groups per tile).  Two 4 KiB staging tiles S0 / S1 (1024-byte aligned, XOR swizzle == TMA 128-byte swizzle):
+//   BIAS_GELU : act -> S0, Linear output -> S1, both TMA stores issued back to back.
+//   DGELU     : aux (pre-activation h) arrives in S1 by a TMA load issued one group ahead; result -> S0 -> TMA store.
+//   GATE_RES  : aux (residual x) in S1 as above; x + gate*out -> S0 -> store, then the Linear output through S0 again.
+// Every wait on a store's shared-memory read sits behind a full group of math, so it is normally free.
+template <int EPI>
+__device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUtensorMap* tmC, const CUtensorMap* tmC2,
+                                                    const CUtensorMap* tmAux, uint8_t* S0, uint32_t aux_bar,
+                                                    uint32_t tmem_base, uint32_t tfull_bar0, uint32_t leader_tempty0,
+                                                    int tile0, int tile_step, int total_tiles, int m_pairs, int n_tiles,
+                                                    int crank, int q, int chalf, int lane) {
+  constexpr bool kAux = (EPI == VDS_EPI_GATE_RES || EPI == VDS_EPI_DGELU);
+  uint8_t* S1 = S0 + 4096;
+  const uint32_t s0 = smem_u32(S0), s1 = smem_u32(S1);
+  auto row_of = [&](int tile) { return ((tile % m_pairs) * 2 + crank) * BM + q * 32; };
+  auto col_of = [&](int tile, int gi) { return ((tile / m_pairs) % n_tiles) * G2_BN + (chalf * 2 + gi) * 64; };
+  uint32_t aux_phase = 0;
+  if (kAux && tile0 < total_tiles && lane == 0) {
+    mbar_expect_tx(aux_bar, 4096);
+    tma_load_2d(s1, tmAux, aux_bar, col_of(tile0, 0), row_of(tile0));
+  }
+  const bool has_bias = (EPI != VDS_EPI_DGELU) && p.bias != nullptr;
+  int it = 0;
+  for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+    const int acc = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1u;
+    mbar_wait(tfull_bar0 + 8u * acc, acc_phase);
+    tc_fence_after();
+    const int row0 = row_of(tile);
+    const uint32_t t_base = tmem_base + acc * G2_BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int gi = 0; gi < 2; ++gi) {
+      const int col0 = col_of(tile, gi);
+      uint32_t r0[32], r1[32];
+      tmem_ld32(t_base + (chalf * 2 + gi) * 64, r0);
+      tmem_ld32(t_base + (chalf * 2 + gi) * 64 + 32, r1);
+      tmem_ld_wait();
+      if (gi == 1) {   // accumulator buffer drained: the MMA warp may start the tile after next
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
+      }
+      uint4 xa[8];      // aux row of this thread, later the primary output
+      if constexpr (kAux) {
+        mbar_wait(aux_bar, aux_phase);
+        aux_phase ^= 1u;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) xa[g] = *reinterpret_cast<const uint4*>(S1 + stg_off(lane, g));
+        __syncwarp();
+        // prefetch the aux tile of the next group (this tile's second group or the next tile's first)
+        const bool more = gi == 0 || tile + tile_step < total_tiles;
+        if (more && lane == 0) {
+          const int nt_tile = gi == 0 ? tile : tile + tile_step, ngi = gi == 0 ? 1 : 0;
+          mbar_expect_tx(aux_bar, 4096);
+          tma_load_2d(s1, tmAux, aux_bar, col_of(nt_tile, ngi), row_of(nt_tile));
+        }
+      }
+      uint4 keep[8];    // second output (bf16 Linear result)
+      const int b = (EPI == VDS_EPI_GATE_RES) ? min(row0 + lane, p.M - 1) / p.rows_per_batch : 0;
+      uint4 bnext = make_uint4(0u, 0u, 0u, 0u), gnext = make_uint4(0u, 0u, 0u, 0u);
+      if (has_bias) bnext = __ldg(reinterpret_cast<const uint4*>(p.bias + col0));
+      if constexpr (EPI == VDS_EPI_GATE_RES)
+        gnext = __ldg(reinterpret_cast<const uint4*>(p.gate + (long long)b * p.gate_stride + col0));
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 braw = bnext, graw = gnext;
+        if (g < 7) {   // per-column operands one chunk ahead (L1-resident after the first warp touched them)
+          if (has_bias) bnext = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + (g + 1) * 8));
+          if constexpr (EPI == VDS_EPI_GATE_RES)
+            gnext = __ldg(reinterpret_cast<const uint4*>(p.gate + (long long)b * p.gate_stride + col0 + (g + 1) * 8));
+        }
+        float a8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a8[j] = __uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]);
+        if (has_bias) {
+          float bb[8];
+          unpack8(braw, bb);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float2 t = add2(make_float2(a8[j], a8[j + 1]), make_float2(bb[j], bb[j + 1]));
+            a8[j] = t.x; a8[j + 1] = t.y;
+          }
+        }
+        if constexpr (EPI == VDS_EPI_BIAS_GELU) {
+          float act[8];
+          keep[g] = pack8(a8);                                // bf16 Linear output (what the reference's GELU sees)
+          unpack8(keep[g], a8);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float2 a2 = gelu_erf2(make_float2(a8[j], a8[j + 1]));
+            act[j] = a2.x; act[j + 1] = a2.y;
+          }
+          xa[g] = pack8(act);
+        } else if constexpr (EPI == VDS_EPI_GATE_RES) {
+          float g8[8], x8[8], o8[8];
+          unpack8(graw, g8);
+          unpack8(xa[g], x8);
+          keep[g] = pack8(a8);                                // Linear output is bf16 in the reference
+          unpack8(keep[g], a8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o8[j] = x8[j] + bf16_round(a8[j] * g8[j]);   // x + (out * gate), each op rounded
+          xa[g] = pack8(o8);
+        } else {   // DGELU
+          float h8[8];
+          unpack8(xa[g], h8);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const float2 d2 = mul2(make_float2(a8[j], a8[j + 1]), dgelu_erf2(make_float2(h8[j], h8[j + 1])));
+            a8[j] = d2.x; a8[j + 1] = d2.y;
+          }
+          xa[g] = pack8(a8);
+        }
+      }
+      // staging tiles are free once the previous group's stores have been read out (issued a whole group ago)
+      if (lane == 0) bulk_wait_group_read0();
+      __syncwarp();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(S0 + stg_off(lane, g)) = xa[g];
+      if constexpr (EPI == VDS_EPI_BIAS_GELU) {
+        if (p.C != nullptr) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(S1 + stg_off(lane, g)) = keep[g];
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (EPI == VDS_EPI_DGELU) {
+          tma_store_2d(tmC, s0, col0, row0);
+        } else {
+          tma_store_2d(tmC2, s0, col0, row0);
+          if (EPI == VDS_EPI_BIAS_GELU && p.C != nullptr) tma_store_2d(tmC, s1, col0, row0);
+        }
+        bulk_commit_group();
+      }
+      if constexpr (EPI == VDS_EPI_GATE_RES) {
+        if (p.C != nullptr) {   // S1 is the aux landing tile, so the Linear output reuses S0 after its first store was read
+          if (lane == 0) bulk_wait_group_read0();
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(S0 + stg_off(lane, g)) = keep[g];
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(tmC, s0, col0, row0); bulk_commit_group(); }
+        }
+      }
+    }
+  }
+  if (lane == 0) bulk_wait_group0();   // all stores complete before the CTA may exit
+}
+
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmDev p,
-             long long* dbg, int tma_c, int tma_c2) {
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+             const __grid_constant__ CUtensorMap tmAux, const GemmDev p, long long* dbg, int tma_c, int tma_c2,
+             int fast) {
+  constexpr int G2_STAGES = G2Cfg<EPI>::stages;
+  constexpr int G2_STG = 8 * G2Cfg<EPI>::stg_warp;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
   const uint32_t bar_base = smem_base + G2_STAGES * G2_STAGE + G2_STG;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (G2_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * G2_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * G2_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * G2_STAGES + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (G2_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * G2_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * G2_MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * G2_MAX_STAGES + 4);
+  auto aux_bar = [&](int w) { return bar_base + 8u * (2 * G2_MAX_STAGES + 5 + w); };   // one per epilogue warp
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + G2_STAGES * G2_STAGE + G2_STG + 8 * (2 * G2_STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + G2_STAGES * G2_STAGE + G2_STG + 8 * (2 * G2_MAX_STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crank = (int)cluster_ctarank();
@@ -101,6 +267,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(tfull_bar(a), 1);   // leader's MMA commit, multicast
       mbar_init(tempty_bar(a), 16); // 8 epilogue warps x 2 CTAs arrive on the LEADER's barrier
     }
+    for (int w = 0; w < 8; ++w) mbar_init(aux_bar(w), 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -211,7 +378,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t leader_tempty0 = mapa_rank(tempty_bar(0), 0);
     int it = 0;
     long long e_wait = 0, e_busy = 0, e_tmem = 0, e_grp = 0;
-    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+    if constexpr (G2Cfg<EPI>::fused) {
+      if (fast) {
+        fused_epilogue_warp<EPI>(p, &tmC, &tmC2, &tmAux, smem_gen + G2_STAGES * G2_STAGE + (warp - 2) * 8192,
+                                 aux_bar(warp - 2), tmem_base, tfull_bar(0), leader_tempty0, tile0, tile_step, total_tiles,
+                                 m_pairs, n_tiles, crank, q, chalf, lane);
+        it = -1;
+      }
+    }
+    for (int tile = tile0; it >= 0 && tile < total_tiles; tile += tile_step, ++it) {
       const int mt = (tile % m_pairs) * 2 + crank;
       const int nt = (tile / m_pairs) % n_tiles;
       const int acc = it & 1;
@@ -306,6 +481,31 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
       tma_c2 = 1;
     }
   }
+  // fused fast path: every bf16 operand / output of the epilogue reachable by TMA (no row remap, 16-byte aligned)
+  CUtensorMap tmAux = tmA;
+  int fast = 0;
+  if (G2Cfg<EPI>::fused && a.remap_rows == 0) {
+    auto ok = [](const void* ptr, long long ld) { return ptr != nullptr && ld % 8 == 0 && ((uintptr_t)ptr & 15) == 0; };
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M}, strides[1];
+    uint32_t box[2] = {64, 32};
+    auto enc = [&](CUtensorMap* tm, const void* ptr, long long ld) {
+      strides[0] = (uint64_t)ld * 2;
+      return encode_tmap_bf16(tm, ptr, 2, dims, strides, box);
+    };
+    const bool need_aux = EPI != VDS_EPI_BIAS_GELU;
+    const bool main_c2 = EPI != VDS_EPI_DGELU;   // primary output is C2 (act / residual stream), C for dGELU
+    bool good = main_c2 ? ok(a.C2, a.ldc2) : ok(a.C, a.ldc);
+    if (main_c2 && a.C != nullptr) good = good && ok(a.C, a.ldc);
+    if (need_aux) good = good && ok(a.aux, a.ldaux);
+    if (good) {
+      int r = 0;
+      if (main_c2) r = enc(&tmC2, a.C2, a.ldc2);
+      if (!r && a.C != nullptr) r = enc(&tmC, a.C, a.ldc);
+      if (!r && need_aux) r = enc(&tmAux, a.aux, a.ldaux);
+      if (r) return r;
+      fast = 1;
+    }
+  }
   GemmDev p;
   p.M = a.M; p.N = a.N; p.K = a.K;
   const int k_iters = (a.K + BK - 1) / BK;
@@ -346,7 +546,7 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, p, g_gemm2_trace, tma_c, tma_c2);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, tmAux, p, g_gemm2_trace, tma_c, tma_c2, fast);
   if (e != cudaSuccess) {
     set_error("gemm2: cluster launch failed: %s", cudaGetErrorString(e));
     return VDS_ERR_CUDA;
