@@ -103,11 +103,15 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
     tma_load_2d(s1, tmAux, aux_bar, col_of(tile0, 0), row_of(tile0));
   }
   const bool has_bias = (EPI != VDS_EPI_DGELU) && p.bias != nullptr;
+  const bool trace = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
+  long long c_tf = 0, c_ld = 0, c_aux = 0, c_math = 0, c_rd = 0, c_sts = 0, c_st = 0;
   int it = 0;
   for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
     const int acc = it & 1;
     const uint32_t acc_phase = (it >> 1) & 1u;
+    long long tq = clock64();
     mbar_wait(tfull_bar0 + 8u * acc, acc_phase);
+    c_tf += clock64() - tq;
     tc_fence_after();
     const int row0 = row_of(tile);
     const uint32_t t_base = tmem_base + acc * G2_BN + (static_cast<uint32_t>(q * 32) << 16);
@@ -115,15 +119,18 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
     for (int gi = 0; gi < 2; ++gi) {
       const int col0 = col_of(tile, gi);
       uint32_t r0[32], r1[32];
+      tq = clock64();
       tmem_ld32(t_base + (chalf * 2 + gi) * 64, r0);
       tmem_ld32(t_base + (chalf * 2 + gi) * 64 + 32, r1);
       tmem_ld_wait();
+      c_ld += clock64() - tq;
+      tq = clock64();
       if (gi == 1) {   // accumulator buffer drained: the MMA warp may start the tile after next
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
       }
-      uint4 xa[8];      // aux row of this thread, later the primary output
+      uint4 xa[8];      // aux row of this thread
       if constexpr (kAux) {
         mbar_wait(aux_bar, aux_phase);
         aux_phase ^= 1u;
@@ -138,6 +145,8 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
           tma_load_2d(s1, tmAux, aux_bar, col_of(nt_tile, ngi), row_of(nt_tile));
         }
       }
+      c_aux += clock64() - tq;
+      tq = clock64();
       uint4 keep[8];    // second output (bf16 Linear result)
       const int b = (EPI == VDS_EPI_GATE_RES) ? min(row0 + lane, p.M - 1) / p.rows_per_batch : 0;
       uint4 bnext = make_uint4(0u, 0u, 0u, 0u), gnext = make_uint4(0u, 0u, 0u, 0u);
@@ -152,6 +161,7 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
           if constexpr (EPI == VDS_EPI_GATE_RES)
             gnext = __ldg(reinterpret_cast<const uint4*>(p.gate + (long long)b * p.gate_stride + col0 + (g + 1) * 8));
         }
+        uint4 outv;
         float a8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) a8[j] = __uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]);
@@ -165,15 +175,10 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
           }
         }
         if constexpr (EPI == VDS_EPI_BIAS_GELU) {
-          float act[8];
           keep[g] = pack8(a8);                                // bf16 Linear output (what the reference's GELU sees)
           unpack8(keep[g], a8);
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            const float2 a2 = gelu_erf2(make_float2(a8[j], a8[j + 1]));
-            act[j] = a2.x; act[j + 1] = a2.y;
-          }
-          xa[g] = pack8(act);
+          gelu_erf8(a8);
+          outv = pack8(a8);
         } else if constexpr (EPI == VDS_EPI_GATE_RES) {
           float g8[8], x8[8], o8[8];
           unpack8(graw, g8);
@@ -182,31 +187,29 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
           unpack8(keep[g], a8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o8[j] = x8[j] + bf16_round(a8[j] * g8[j]);   // x + (out * gate), each op rounded
-          xa[g] = pack8(o8);
+          outv = pack8(o8);
         } else {   // DGELU
           float h8[8];
           unpack8(xa[g], h8);
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) {
-            const float2 d2 = mul2(make_float2(a8[j], a8[j + 1]), dgelu_erf2(make_float2(h8[j], h8[j + 1])));
-            a8[j] = d2.x; a8[j + 1] = d2.y;
-          }
-          xa[g] = pack8(a8);
+          dgelu_mul8(a8, h8);
+          outv = pack8(a8);
         }
-      }
-      // staging tiles are free once the previous group's stores have been read out (issued a whole group ago)
-      if (lane == 0) bulk_wait_group_read0();
-      __syncwarp();
-#pragma unroll
-      for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(S0 + stg_off(lane, g)) = xa[g];
-      if constexpr (EPI == VDS_EPI_BIAS_GELU) {
-        if (p.C != nullptr) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) *reinterpret_cast<uint4*>(S1 + stg_off(lane, g)) = keep[g];
+        // Results leave the registers chunk by chunk (short live ranges keep ptxas from serialising the math pair by
+        // pair).  The staging tiles were handed to the TMA store of the previous group one TMEM load and one chunk of
+        // math ago; its shared-memory read has normally finished by now.
+        if (g == 0) {
+          if (lane == 0) bulk_wait_group_read0();
+          __syncwarp();
         }
+        *reinterpret_cast<uint4*>(S0 + stg_off(lane, g)) = outv;
+        if constexpr (EPI == VDS_EPI_BIAS_GELU) *reinterpret_cast<uint4*>(S1 + stg_off(lane, g)) = keep[g];
       }
+      c_math += clock64() - tq;
+      tq = clock64();
       fence_proxy_async_smem();
       __syncwarp();
+      c_sts += clock64() - tq;
+      tq = clock64();
       if (lane == 0) {
         if constexpr (EPI == VDS_EPI_DGELU) {
           tma_store_2d(tmC, s0, col0, row0);
@@ -227,11 +230,16 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
           if (lane == 0) { tma_store_2d(tmC, s0, col0, row0); bulk_commit_group(); }
         }
       }
+      c_st += clock64() - tq;
     }
+  }
+  if (trace) {
+    p.dbg[8] = c_tf; p.dbg[9] = c_ld; p.dbg[10] = c_aux; p.dbg[11] = c_math; p.dbg[12] = c_rd; p.dbg[13] = c_sts; p.dbg[14] = c_st;
   }
   if (lane == 0) bulk_wait_group0();   // all stores complete before the CTA may exit
 }
 
+// (10 warps = 3 on two of the SM sub-partitions: 3 x 32 x regs <= 16K caps the kernel at 168 registers per thread)
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,

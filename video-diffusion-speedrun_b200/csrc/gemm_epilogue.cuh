@@ -74,6 +74,61 @@ __device__ __forceinline__ float2 dgelu_erf2(float2 x) {
   const float2 omr = fma2(splat2(-1.0f), r, splat2(1.0f));
   return fma2(mul2(x, w), mul2(r, omr), r);
 }
+// Eight elements at a time, written in phases (all polynomials, all ex2, all 1+e, all rcp): the MUFU results are
+// consumed ~8 issue slots after they were requested, so one warp hides the MUFU latency by itself (pair-at-a-time
+// code stalled twice per pair, which made the epilogue latency- instead of issue-bound).
+__device__ __forceinline__ void phi_logistic8(const float2 (&x)[4], const float2 (&s)[4], float2 (&r)[4]) {
+  float2 t[4], d[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 q = fma2(splat2(VDS_GELU_Q4), s[k], splat2(VDS_GELU_Q3));
+    q = fma2(q, s[k], splat2(VDS_GELU_Q2));
+    q = fma2(q, s[k], splat2(VDS_GELU_Q1));
+    q = fma2(q, s[k], splat2(VDS_GELU_Q0));
+    t[k] = mul2(x[k], q);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t[k] = make_float2(ex2(t[k].x), ex2(t[k].y));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) d[k] = add2(t[k], splat2(1.0f));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r[k] = make_float2(rcp_approx(d[k].x), rcp_approx(d[k].y));
+}
+// v[0..7] <- gelu(v)
+__device__ __forceinline__ void gelu_erf8(float (&v)[8]) {
+  float2 x[4], s[4], r[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { x[k] = make_float2(v[2 * k], v[2 * k + 1]); s[k] = mul2(x[k], x[k]); }
+  phi_logistic8(x, s, r);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const float2 g = mul2(x[k], r[k]); v[2 * k] = g.x; v[2 * k + 1] = g.y; }
+}
+// a[0..7] <- a * gelu'(h)
+__device__ __forceinline__ void dgelu_mul8(float (&a)[8], const float (&h)[8]) {
+  float2 x[4], s[4], r[4], w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    x[k] = make_float2(h[2 * k], h[2 * k + 1]);
+    const float2 sq = mul2(x[k], x[k]);
+    s[k] = make_float2(fminf(sq.x, 64.0f), fminf(sq.y, 64.0f));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 ww = fma2(splat2(VDS_GELU_W4), s[k], splat2(VDS_GELU_W3));
+    ww = fma2(ww, s[k], splat2(VDS_GELU_W2));
+    ww = fma2(ww, s[k], splat2(VDS_GELU_W1));
+    ww = fma2(ww, s[k], splat2(VDS_GELU_W0));
+    w[k] = mul2(x[k], ww);
+  }
+  phi_logistic8(x, s, r);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 omr = fma2(splat2(-1.0f), r[k], splat2(1.0f));
+    const float2 dg = fma2(w[k], mul2(r[k], omr), r[k]);
+    const float2 o = mul2(make_float2(a[2 * k], a[2 * k + 1]), dg);
+    a[2 * k] = o.x; a[2 * k + 1] = o.y;
+  }
+}
 __device__ __forceinline__ float gelu_erf(float x) { return gelu_erf2(make_float2(x, x)).x; }
 __device__ __forceinline__ float dgelu_erf(float x) { return dgelu_erf2(make_float2(x, x)).x; }
 
