@@ -171,25 +171,70 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int valid = p.Lk - j * 128;             // columns >= valid are padding (last tile only)
       mbar_wait(s_full + 8 * t, j & 1);
       tc_fence_after();
-      // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is reduced
-      float mx = -INFINITY;
       uint32_t va[32], vb[32];
-      tmem_ld32(tS, va);
+      float mxs;
+      if (j > 0 && valid >= 128) {
+        // Speculative single pass: exponentiate against the running max of the previous tiles while tracking this
+        // tile's max.  The lazy-rescale rule (rescale only when the max grows by more than 2^8) is the same as in the
+        // two-pass path below, so in the common case — no row of the warp needs a rescale — S is read from TMEM once
+        // and the max is off the critical path.  P stays in registers until that is known (it overwrites S).
+        uint32_t pk[64];
+        const float nm0 = -m_run;
+        float2 s2 = make_float2(0.f, 0.f);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        tmem_ld32(tS, va);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t (&v)[32] = (c & 1) ? vb : va;
-        tmem_ld_wait();
-        if (c < 3) tmem_ld32(tS + (c + 1) * 32, (c & 1) ? va : vb);
-        if (valid >= 128) {
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&v)[32] = (c & 1) ? vb : va;
+          tmem_ld_wait();
+          if (c < 3) tmem_ld32(tS + (c + 1) * 32, (c & 1) ? va : vb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 2) {
+            const float2 x = fma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                                  make_float2(sl2, sl2), make_float2(nm0, nm0));
+            mx0 = fmaxf(mx0, x.x);
+            mx1 = fmaxf(mx1, x.y);
+            const float2 pe = make_float2(ex2(x.x), ex2(x.y));
+            s2 = add2(s2, pe);
+            pk[c * 16 + (i >> 1)] = pack_bf16x2(pe.x, pe.y);
+          }
         }
+        const float mxx = fmaxf(mx0, mx1);          // max of (s * scale_log2 - m_run)
+        if (!__any_sync(0xffffffffu, mxx > 8.0f)) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pc[i] = pk[c * 16 + i];
+            tmem_st16(tS + c * 16, pc);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(p_full + 8 * t);
+          l_run += s2.x + s2.y;
+          continue;
+        }
+        mxs = m_run + mxx;                           // some row needs the rescale: redo the tile on the exact path
+      } else {
+        // TMEM loads are software-pipelined: chunk c+1 is in flight while chunk c is reduced
+        float mx = -INFINITY;
+        tmem_ld32(tS, va);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&v)[32] = (c & 1) ? vb : va;
+          tmem_ld_wait();
+          if (c < 3) tmem_ld32(tS + (c + 1) * 32, (c & 1) ? va : vb);
+          if (valid >= 128) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
+        }
+        mxs = mx * sl2;
       }
-      const float mxs = mx * sl2;
       float alpha = 1.0f;
       const bool need = mxs > m_run + 8.0f;         // lazy: p stays <= 2^8 otherwise
       if (need) {
