@@ -38,3 +38,57 @@ def test_context_kv_cache_is_bit_identical(cuda_dev):
     b = denoise(model, ctx, inference_steps=3, latents=lat0, device=cuda_dev, cache_context_kv=True)
     assert torch.equal(a, b)
     assert model._ckv_cache is None
+
+
+def test_graphed_denoiser_bit_identical_to_eager(cuda_dev):
+    """§8f n1: the CUDA-graph replay of the denoising step must reproduce the eager loop exactly (same kernels, same
+    RNG consumption: 6 RoPE draws per step in the order cond h,w,t then uncond h,w,t)."""
+    from vds_b200.sampling.sample import GraphedDenoiser, denoise
+    fx, cfg, model, (latent, noise, context, t) = golden_case("tiny_nobias")
+    model = model.to(cuda_dev, torch.bfloat16).eval()
+    lat0, ctx = noise.to(cuda_dev), context.to(cuda_dev)
+    steps = 5
+    torch.manual_seed(21)
+    ref = denoise(model, ctx, inference_steps=steps, cfg_scale=6.0, latents=lat0, device=cuda_dev)
+    rng_after_eager = torch.get_rng_state()
+    g = GraphedDenoiser(model, ctx, tuple(lat0.shape), cfg_scale=6.0, device=cuda_dev)
+    torch.manual_seed(21)
+    got = g.run(lat0, inference_steps=steps)
+    assert g.graph is not None and g.launches_per_step > 0
+    assert torch.equal(torch.get_rng_state(), rng_after_eager)
+    assert torch.equal(got, ref)
+    # a second run replays the already-captured graph from the first step on
+    torch.manual_seed(21)
+    again = g.run(lat0, inference_steps=steps)
+    assert torch.equal(again, ref)
+    assert model._ckv_cache is None
+
+
+def test_graphed_denoiser_batched_cfg(cuda_dev):
+    """batch_cfg=True: cond and uncond as one 2B forward sharing one RoPE draw per step.  Reference for this mode:
+    the eager model called twice per step with the RNG rewound in between (same offsets for both halves)."""
+    from vds_b200.sampling.sample import GraphedDenoiser, shift_time
+    fx, cfg, model, (latent, noise, context, t) = golden_case("tiny_nobias")
+    model = model.to(cuda_dev, torch.bfloat16).eval()
+    lat0, ctx = noise.to(cuda_dev), context.to(cuda_dev)
+    steps, scale = 4, 6.0
+    torch.manual_seed(5)
+    acc = lat0.float()
+    lat = lat0.clone()
+    with torch.no_grad():
+        for i in range(steps, 0, -1):
+            tcur = shift_time(i / steps)
+            dt = tcur - shift_time((i - 1) / steps)
+            tt = torch.tensor([tcur] * lat.shape[0]).to(cuda_dev, torch.bfloat16)
+            st = torch.get_rng_state()
+            c_out = model(lat, ctx, tt)
+            torch.set_rng_state(st)
+            u_out = model(lat, torch.zeros_like(ctx), tt)
+            out = u_out + scale * (c_out - u_out)
+            acc = acc + dt * out.float()
+            lat = acc.to(torch.bfloat16)
+    g = GraphedDenoiser(model, ctx, tuple(lat0.shape), cfg_scale=scale, device=cuda_dev, batch_cfg=True)
+    torch.manual_seed(5)
+    got = g.run(lat0, inference_steps=steps)
+    err = (got - acc).abs().max().item() / (acc.abs().max().item() + 1e-6)
+    assert err < 2e-2, err

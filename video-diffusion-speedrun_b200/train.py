@@ -82,9 +82,7 @@ class GraphedTrainStep:
         self.context = torch.zeros(context_shape, **bf)
         self.t = torch.zeros((latent_shape[0],), **bf)
         self.starts_dev = torch.zeros(3, device=dev, dtype=torch.int32)
-        self.starts_host = torch.zeros(3, dtype=torch.int32).pin_memory()
         self.hyper_dev = torch.zeros(34, device=dev, dtype=torch.float32)
-        self.hyper_host = torch.zeros(34, dtype=torch.float32).pin_memory()
         B, C, T, H, W = latent_shape
         self.thw = (T // model.time_patch_size, H // model.patch_size, W // model.patch_size)
         self.graph = None
@@ -96,10 +94,11 @@ class GraphedTrainStep:
 
     def _refresh_scalars(self):
         st, sh, sw = self._engine.draw_rope_starts(self.model.rope, self.thw)   # consumes the CPU RNG like the reference
-        self.starts_host[0], self.starts_host[1], self.starts_host[2] = st, sh, sw
-        self.starts_dev.copy_(self.starts_host, non_blocking=True)
-        self.hyper_host.copy_(torch.tensor(self.opt.hyper_values(self.opt._step + 1), dtype=torch.float32))
-        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
+        # Fresh pinned staging tensors every step: torch's caching host allocator does not hand a block out again
+        # before the async copy that reads it has run, so the host may queue many steps ahead of the GPU.
+        self.starts_dev.copy_(torch.tensor([st, sh, sw], dtype=torch.int32).pin_memory(), non_blocking=True)
+        hyper = torch.tensor(self.opt.hyper_values(self.opt._step + 1), dtype=torch.float32).pin_memory()
+        self.hyper_dev.copy_(hyper, non_blocking=True)
 
     def _step_body(self):
         """The step without torch.autograd in the loop (the engine's forward / backward are called directly), so the
