@@ -1,0 +1,38 @@
+"""Host-side input pipeline: DistributedSampler-equivalent index sharding."""
+import torch
+
+import vds_b200  # noqa: F401
+from vds_b200.data import batches, shard_indices
+
+
+def test_shard_indices_partition_and_match_torch_sampler():
+    from torch.utils.data.distributed import DistributedSampler
+    n, world = 103, 4
+    ds = list(range(n))
+    for epoch in (0, 3):
+        got = [shard_indices(n, r, world, seed=7, epoch=epoch) for r in range(world)]
+        assert len({len(g) for g in got}) == 1 and len(got[0]) == (n + world - 1) // world
+        assert set().union(*map(set, got)) == set(range(n))          # every sample seen (tail padded by wrap-around)
+        for r in range(world):
+            s = DistributedSampler(ds, num_replicas=world, rank=r, shuffle=True, seed=7)
+            s.set_epoch(epoch)
+            assert list(iter(s)) == got[r]
+    # drop_last: disjoint, equal-sized, no padding
+    got = [shard_indices(n, r, world, seed=1, drop_last=True) for r in range(world)]
+    flat = sum(got, [])
+    assert len(flat) == (n // world) * world and len(set(flat)) == len(flat)
+    assert shard_indices(10, 1, 2, shuffle=False) == [1, 3, 5, 7, 9]
+    assert shard_indices(0, 0, 2) == []
+
+
+def test_batches():
+    idx = list(range(10))
+    assert batches(idx, 4) == [[0, 1, 2, 3], [4, 5, 6, 7]]
+    assert batches(idx, 4, drop_last=False)[-1] == [8, 9]
+
+
+def test_prefetcher_refuses_cpu():
+    import pytest
+    from vds_b200.data import DevicePrefetcher
+    with pytest.raises(RuntimeError):
+        DevicePrefetcher([], device="cpu")
