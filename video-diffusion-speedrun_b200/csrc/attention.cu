@@ -94,6 +94,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  pdl_wait();      // everything above is launch-independent set-up; global inputs may come from the previous kernel
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -324,6 +326,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // delta[b, head, row] = sum_d dO * O   (fp32)
 __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, long long ldo,
                                      long long lddo, float* __restrict__ delta, int B, int L, int nh) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)B * L * nh;
   if (gw >= total) return;
@@ -455,6 +459,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmDQ);
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  pdl_wait();      // everything above is launch-independent set-up; global inputs may come from the previous kernel
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -761,6 +767,8 @@ long long* g_attn_bwd_trace = nullptr;   // set through vds_debug_attn_bwd_trace
 __global__ void __launch_bounds__(256) attn_bwd_tail_fixup_kernel(const float* __restrict__ compact, bf16* __restrict__ dk,
                                                                   long long lddk, bf16* __restrict__ dv, long long lddv,
                                                                   int item_base, int kv_tiles, int nh, int Lk) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const int item = item_base + blockIdx.x;
   const int kv_tile = item % kv_tiles, head = (item / kv_tiles) % nh, b = item / (kv_tiles * nh);
   const float* src = compact + (long long)blockIdx.x * 2 * 128 * HD;
@@ -826,7 +834,7 @@ int vds_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   p.out = (bf16*)out; p.ldo = ldo; p.lse = lse; p.Lq = Lq; p.Lk = Lk; p.nh = nh;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((Lq + 255) / 256, nh, B);
-  attn_fwd_kernel<<<grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  launch_k(attn_fwd_kernel, grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream, tq, tk, tv, p);
   VDS_CHECK_LAUNCH("attn_fwd");
   return VDS_OK;
 }
@@ -862,7 +870,7 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   }
   {
     const long long warps = (long long)B * Lq * nh;
-    attn_bwd_prep_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(attn_bwd_prep_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream, 
         (const bf16*)o, (const bf16*)d_o, ldo, lddo, delta, B, Lq, nh);
     VDS_CHECK_LAUNCH("attn_bwd_prep");
   }
@@ -892,16 +900,16 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   }
   if (tail_s == 0) {
     p.item_base = 0;
-    attn_bwd_kernel<<<total * q_splits, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, tdo, tdq, p);
+    launch_k(attn_bwd_kernel, total * q_splits, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream, tq, tk, tv, tdo, tdq, p);
   } else {
     p.item_base = 0;
-    attn_bwd_kernel<<<full, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, tdo, tdq, p);
+    launch_k(attn_bwd_kernel, full, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream, tq, tk, tv, tdo, tdq, p);
     VDS_CHECK_LAUNCH("attn_bwd");
     cudaMemsetAsync(tail_ws, 0, (size_t)rem * 2 * 128 * HD * 4, (cudaStream_t)stream);
     p.item_base = full; p.q_splits = tail_s; p.compact_acc = (float*)tail_ws;
-    attn_bwd_kernel<<<rem * tail_s, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(tq, tk, tv, tdo, tdq, p);
+    launch_k(attn_bwd_kernel, rem * tail_s, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream, tq, tk, tv, tdo, tdq, p);
     VDS_CHECK_LAUNCH("attn_bwd");
-    attn_bwd_tail_fixup_kernel<<<rem, 256, 0, (cudaStream_t)stream>>>((const float*)tail_ws, (bf16*)dk, lddk, (bf16*)dv,
+    launch_k(attn_bwd_tail_fixup_kernel, rem, 256, 0, (cudaStream_t)stream, (const float*)tail_ws, (bf16*)dk, lddk, (bf16*)dv,
                                                                       lddv, full, kv_tiles, nh, Lk);
   }
   VDS_CHECK_LAUNCH("attn_bwd");

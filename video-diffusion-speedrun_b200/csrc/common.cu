@@ -1,5 +1,7 @@
 #include "common.h"
 
+#include <stdlib.h>
+
 #include <stdarg.h>
 
 #include <atomic>
@@ -17,6 +19,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VDS_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
 
 int num_sms() {
   static int sms = 0;

@@ -32,6 +32,8 @@ __device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
 __global__ void patchify_kernel(const bf16* __restrict__ x, const bf16* __restrict__ noise,
                                 const bf16* __restrict__ tvals, bf16* __restrict__ out, int B, int C, int T,
                                 int H, int W, int p, int pt) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const long long total = (long long)B * C * T * H * W;
   const int Tp = T / pt, Hp = H / p, Wp = W / p;
   const int Kf = C * pt * p * p;
@@ -60,6 +62,8 @@ __global__ void patchify_kernel(const bf16* __restrict__ x, const bf16* __restri
 // (model.py:392-401).  `to_tokens` = backward direction (gather dOut into token rows).
 __global__ void unpatchify_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int B, int C, int T, int H,
                                   int W, int p, int pt, int to_tokens) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const long long total = (long long)B * C * T * H * W;
   const int Tp = T / pt, Hp = H / p, Wp = W / p;
   const int F = C * pt * p * p;
@@ -87,6 +91,8 @@ template <typename TT>
 __global__ void rope_rows_kernel(const TT* __restrict__ tcos, const TT* __restrict__ tsin, float* __restrict__ ocos,
                                  float* __restrict__ osin, int L, int D, int n_reg, int Tp, int Hp, int Wp,
                                  int st, int sh, int sw, int hmax, int wmax, const int* __restrict__ starts_dev) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   if (starts_dev != nullptr) {   // CUDA-graph replays: the (t, h, w) offsets of this step live in device memory
     st = starts_dev[0];
     sh = starts_dev[1];
@@ -115,6 +121,8 @@ __global__ void rope_rows_kernel(const TT* __restrict__ tcos, const TT* __restri
 // out[b, :half] = cos(t*f_i), out[b, half:] = sin(t*f_i), f_i = exp(-ln(max_period)*i/half)  (model.py:12-22)
 __global__ void timestep_embedding_kernel(const bf16* __restrict__ t, bf16* __restrict__ out, int B, int dim,
                                           float max_period) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -127,6 +135,8 @@ __global__ void timestep_embedding_kernel(const bf16* __restrict__ t, bf16* __re
 
 // ------------------------------------------------------------------------------------- SiLU
 __global__ void silu_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = __bfloat162float(x[i]);
@@ -135,6 +145,8 @@ __global__ void silu_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, lo
 // dx = dy * silu'(x) (+ dx_add)
 __global__ void silu_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx,
                                 long long n) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = __bfloat162float(x[i]);
@@ -158,6 +170,8 @@ struct NormArgs {
 
 template <int NV>
 __global__ void __launch_bounds__(256) rmsnorm_mod_fwd_kernel(const NormArgs a) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   // Each warp owns RPW consecutive rows: all their 16-byte groups (and the per-sample scale / shift / weight
   // groups) are requested up front, so one DRAM round trip covers RPW rows instead of one.
   constexpr int RPW = (NV <= 3) ? 4 : 2;
@@ -259,6 +273,8 @@ struct NormBwdArgs {
 
 template <int NV, bool HAS_W>
 __global__ void __launch_bounds__(256) rmsnorm_mod_bwd_kernel(const NormBwdArgs a) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   constexpr bool PF = false;  // one-row-ahead prefetch costs more in occupancy than it buys (measured)
   extern __shared__ float red[];  // [8 warps][3][h] would be too big: reduce sequentially below
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -390,6 +406,8 @@ struct GateBwdArgs {
 };
 template <int NV>
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const GateBwdArgs a) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   extern __shared__ float red[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -468,6 +486,8 @@ struct QkvPostArgs {
   int B, L, h, nh, hd;
 };
 __global__ void qkv_post_fwd_kernel(const QkvPostArgs a) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const int half8 = a.hd / 16;                       // 8-element groups in half a head
   const int groups_qk = 2 * a.nh * half8;            // rope groups per token (q and k)
   const int groups_v = (a.v0 != nullptr) ? a.h / 8 : 0;
@@ -525,6 +545,8 @@ struct QkvPostBwdArgs {
   int B, L, h, nh, hd;
 };
 __global__ void qkv_post_bwd_kernel(const QkvPostBwdArgs a) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const int half8 = a.hd / 16;
   const int groups_qk = 2 * a.nh * half8;
   const int groups_v = (a.mode != 0) ? a.h / 8 : 0;
@@ -605,6 +627,8 @@ __global__ void qkv_post_bwd_kernel(const QkvPostBwdArgs a) {
 // the 8 warps meet in shared memory, one atomicAdd per column per CTA.
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, long long rows,
                                                      int n, long long ld, int rows_per_cta) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   __shared__ float red[8][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 256 + lane * 8;
@@ -643,6 +667,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 // out[r, :] (+)= sum_b x[b, r, :]   (register-token gradient: rows 0..15 of every sample)
 __global__ void batch_rowsum_kernel(const bf16* __restrict__ x, float* __restrict__ out, int B, long long batch_stride,
                                     int rows, int h) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * h) return;
   float acc = 0.f;
@@ -652,6 +678,8 @@ __global__ void batch_rowsum_kernel(const bf16* __restrict__ x, float* __restric
 
 // ------------------------------------------------------------------------------------- casts
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n, float scale) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(x + i);
@@ -665,6 +693,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restri
 }
 // y(fp32) (+)= float(x(bf16))
 __global__ void accum_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n, int accumulate) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = __bfloat162float(x[i]);
@@ -682,7 +712,7 @@ int vds_patchify(const void* x, const void* noise, const void* t, void* out, int
   VDS_CHECK_ARG(T % pt == 0 && H % p == 0 && W % p == 0, "patchify: T,H,W must divide by the patch size");
   const long long total = (long long)B * C * T * H * W;
   const int grid = min(ceil_div(total, 256), num_sms() * 16);
-  patchify_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)noise, (const bf16*)t,
+  launch_k(patchify_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)noise, (const bf16*)t,
                                                           (bf16*)out, B, C, T, H, W, p, pt);
   VDS_CHECK_LAUNCH("patchify");
   return VDS_OK;
@@ -693,7 +723,7 @@ int vds_unpatchify(const void* src, void* dst, int B, int C, int T, int H, int W
   VDS_CHECK_ARG(T % pt == 0 && H % p == 0 && W % p == 0, "unpatchify: T,H,W must divide by the patch size");
   const long long total = (long long)B * C * T * H * W;
   const int grid = min(ceil_div(total, 256), num_sms() * 16);
-  unpatchify_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, B, C, T, H, W, p, pt,
+  launch_k(unpatchify_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)src, (bf16*)dst, B, C, T, H, W, p, pt,
                                                             to_tokens);
   VDS_CHECK_LAUNCH("unpatchify");
   return VDS_OK;
@@ -706,10 +736,10 @@ int vds_rope_rows(const void* tcos, const void* tsin, int table_is_bf16, float* 
   const long long total = (long long)L * D;
   const int grid = min(ceil_div(total, 256), num_sms() * 16);
   if (table_is_bf16)
-    rope_rows_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)tcos, (const bf16*)tsin, ocos, osin,
+    launch_k(rope_rows_kernel<bf16>, grid, 256, 0, (cudaStream_t)stream, (const bf16*)tcos, (const bf16*)tsin, ocos, osin,
                                                                   L, D, n_reg, Tp, Hp, Wp, st, sh, sw, hmax, wmax, starts_dev);
   else
-    rope_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)tcos, (const float*)tsin, ocos,
+    launch_k(rope_rows_kernel<float>, grid, 256, 0, (cudaStream_t)stream, (const float*)tcos, (const float*)tsin, ocos,
                                                                    osin, L, D, n_reg, Tp, Hp, Wp, st, sh, sw, hmax,
                                                                    wmax, starts_dev);
   VDS_CHECK_LAUNCH("rope_rows");
@@ -718,19 +748,19 @@ int vds_rope_rows(const void* tcos, const void* tsin, int table_is_bf16, float* 
 
 int vds_timestep_embedding(const void* t, void* out, int B, int dim, float max_period, void* stream) {
   VDS_CHECK_ARG(dim % 2 == 0, "timestep_embedding: odd dim");
-  timestep_embedding_kernel<<<ceil_div((long long)B * dim / 2, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(timestep_embedding_kernel, ceil_div((long long)B * dim / 2, 256), 256, 0, (cudaStream_t)stream, 
       (const bf16*)t, (bf16*)out, B, dim, max_period);
   VDS_CHECK_LAUNCH("timestep_embedding");
   return VDS_OK;
 }
 
 int vds_silu(const void* x, void* y, int64_t n, void* stream) {
-  silu_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n);
+  launch_k(silu_kernel, ceil_div(n, 256), 256, 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, n);
   VDS_CHECK_LAUNCH("silu");
   return VDS_OK;
 }
 int vds_silu_bwd(const void* x, const void* dy, void* dx, int64_t n, void* stream) {
-  silu_bwd_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, n);
+  launch_k(silu_bwd_kernel, ceil_div(n, 256), 256, 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)dy, (bf16*)dx, n);
   VDS_CHECK_LAUNCH("silu_bwd");
   return VDS_OK;
 }
@@ -745,7 +775,7 @@ int vds_rmsnorm_mod_fwd(const void* x, void* y, float* rstd, const void* weight,
   a.rows_out = B * rows_per_batch_out; a.h = h; a.rows_per_batch_out = rows_per_batch_out;
   a.in_batch_stride = in_batch_stride; a.in_row_offset = in_row_offset; a.eps = eps;
   const int nvn = (h + 255) / 256;
-#define VDS_L(NVV) rmsnorm_mod_fwd_kernel<NVV><<<ceil_div(a.rows_out, 8 * ((NVV) <= 3 ? 4 : 2)), 256, 0, (cudaStream_t)stream>>>(a)
+#define VDS_L(NVV) launch_k(rmsnorm_mod_fwd_kernel<NVV>, ceil_div(a.rows_out, 8 * ((NVV) <= 3 ? 4 : 2)), 256, 0, (cudaStream_t)stream, a)
   if (nvn <= 2) VDS_L(2); else if (nvn <= 3) VDS_L(3); else if (nvn <= 5) VDS_L(5); else VDS_L(8);
 #undef VDS_L
   VDS_CHECK_LAUNCH("rmsnorm_mod_fwd");
@@ -773,7 +803,7 @@ int vds_rmsnorm_mod_bwd(const void* dy, const void* x, const float* rstd, const 
     if (8 * h * sizeof(float) > 48 * 1024)                                                                 \
       cudaFuncSetAttribute(rmsnorm_mod_bwd_kernel<NVV, HW>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                            (int)(8 * h * sizeof(float)));                                                  \
-    rmsnorm_mod_bwd_kernel<NVV, HW><<<grid, 256, 8 * h * sizeof(float), (cudaStream_t)stream>>>(a);        \
+    launch_k(rmsnorm_mod_bwd_kernel<NVV, HW>, grid, 256, 8 * h * sizeof(float), (cudaStream_t)stream, a);        \
   } while (0)
   if (weight != nullptr) {
     if (nvn <= 2) VDS_L(2, true); else if (nvn <= 3) VDS_L(3, true); else if (nvn <= 5) VDS_L(5, true); else VDS_L(8, true);
@@ -800,7 +830,7 @@ int vds_gate_bwd(const void* dx, const void* o, const void* gate, void* d_o, flo
     if (8 * h * sizeof(float) > 48 * 1024)                                                                 \
       cudaFuncSetAttribute(gate_bwd_kernel<NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                            (int)(8 * h * sizeof(float)));                                                  \
-    gate_bwd_kernel<NVV><<<grid, 256, 8 * h * sizeof(float), (cudaStream_t)stream>>>(a);                   \
+    launch_k(gate_bwd_kernel<NVV>, grid, 256, 8 * h * sizeof(float), (cudaStream_t)stream, a);                   \
   } while (0)
   if (nvn <= 2) VDS_L(2); else if (nvn <= 3) VDS_L(3); else if (nvn <= 5) VDS_L(5); else VDS_L(8);
 #undef VDS_L
@@ -816,7 +846,7 @@ int vds_qkv_post_fwd(void* qkv, const float* cos, const float* sin, const void* 
   a.lambda = (const bf16*)lambda; a.B = B; a.L = L; a.h = h; a.nh = nh; a.hd = h / nh;
   const long long total = (long long)B * L * (2 * nh * (a.hd / 16) + (v0 ? h / 8 : 0));
   const int grid = min(ceil_div(total, 256), num_sms() * 16);
-  qkv_post_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  launch_k(qkv_post_fwd_kernel, grid, 256, 0, (cudaStream_t)stream, a);
   VDS_CHECK_LAUNCH("qkv_post_fwd");
   return VDS_OK;
 }
@@ -832,7 +862,7 @@ int vds_qkv_post_bwd(void* dqkv, const float* dq_acc, const float* cos, const fl
   a.dv0_acc = dv0_acc; a.mode = mode; a.B = B; a.L = L; a.h = h; a.nh = nh; a.hd = h / nh;
   const long long total = (long long)B * L * (2 * nh * (a.hd / 16) + (mode ? h / 8 : 0));
   const int grid = min(ceil_div(total, 256), num_sms() * 16);
-  qkv_post_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  launch_k(qkv_post_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, a);
   VDS_CHECK_LAUNCH("qkv_post_bwd");
   return VDS_OK;
 }
@@ -843,25 +873,25 @@ int vds_colsum(const void* x, float* out, int64_t rows, int n, int64_t ld, void*
   int row_chunks = max(1, (2 * num_sms()) / col_ctas);
   int rows_per_cta = max(64, ceil_div(rows, row_chunks));
   dim3 grid(col_ctas, ceil_div(rows, rows_per_cta));
-  colsum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, out, rows, n, ld, rows_per_cta);
+  launch_k(colsum_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, out, rows, n, ld, rows_per_cta);
   VDS_CHECK_LAUNCH("colsum");
   return VDS_OK;
 }
 
 int vds_batch_rowsum(const void* x, float* out, int B, int64_t batch_stride, int rows, int h, void* stream) {
-  batch_rowsum_kernel<<<ceil_div((long long)rows * h, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, out, B,
+  launch_k(batch_rowsum_kernel, ceil_div((long long)rows * h, 256), 256, 0, (cudaStream_t)stream, (const bf16*)x, out, B,
                                                                                            batch_stride, rows, h);
   VDS_CHECK_LAUNCH("batch_rowsum");
   return VDS_OK;
 }
 
 int vds_cast_f32_bf16(const float* x, void* y, int64_t n, float scale, void* stream) {
-  cast_f32_bf16_kernel<<<ceil_div(ceil_div(n, 4), 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, n, scale);
+  launch_k(cast_f32_bf16_kernel, ceil_div(ceil_div(n, 4), 256), 256, 0, (cudaStream_t)stream, x, (bf16*)y, n, scale);
   VDS_CHECK_LAUNCH("cast_f32_bf16");
   return VDS_OK;
 }
 int vds_accum_bf16_f32(const void* x, float* y, int64_t n, int accumulate, void* stream) {
-  accum_bf16_f32_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, y, n, accumulate);
+  launch_k(accum_bf16_f32_kernel, ceil_div(n, 256), 256, 0, (cudaStream_t)stream, (const bf16*)x, y, n, accumulate);
   VDS_CHECK_LAUNCH("accum_bf16_f32");
   return VDS_OK;
 }

@@ -69,6 +69,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  pdl_wait();      // everything above is launch-independent set-up; global inputs may come from the previous kernel
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
@@ -275,20 +277,22 @@ static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
   const int max_clusters = num_sms() / CL;
   const int grid = (int)(total < max_clusters ? total : max_clusters) * CL;
   if constexpr (CL == 1) {
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    launch_k(kern, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see common.h: launch_k
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
     if (e != cudaSuccess) {
       set_error("gemm: cluster launch failed: %s", cudaGetErrorString(e));

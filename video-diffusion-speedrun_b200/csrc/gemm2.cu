@@ -281,6 +281,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  pdl_wait();      // everything above is launch-independent set-up; global inputs may come from the previous kernel
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -547,13 +549,15 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
   cfg.blockDim = dim3(G2_THREADS);
   cfg.dynamicSmemBytes = G2_SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see common.h: launch_k
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmC2, tmAux, p, g_gemm2_trace, tma_c, tma_c2, fast);
   if (e != cudaSuccess) {
     set_error("gemm2: cluster launch failed: %s", cudaGetErrorString(e));

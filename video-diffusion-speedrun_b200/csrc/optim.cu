@@ -11,6 +11,8 @@ __global__ void __launch_bounds__(256) loss_kernel(const bf16* __restrict__ x, c
                                                    float* __restrict__ loss_sum, float* __restrict__ loss_batch,
                                                    long long per, int B, float gscale,
                                                    const float* __restrict__ gscale_dev) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const int b = blockIdx.y;
   if (gscale_dev != nullptr) gscale *= *gscale_dev;
   const long long base = (long long)b * per;
@@ -65,6 +67,8 @@ struct AdamArgs {
   const float* hyper_dev;   // optional [lr[16] | wd[16] | bc1 | bc2_sqrt] in device memory (CUDA-graph replays)
 };
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
   const int c = blockIdx.x;
   const long long s = a.chunk_start[c];
   const int n = a.chunk_len[c];
@@ -132,7 +136,7 @@ int vds_loss_fwd_bwd(const void* x, const void* noise, const void* out, void* d_
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   dim3 grid(chunks, B);
-  loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)noise, (const bf16*)out,
+  launch_k(loss_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)noise, (const bf16*)out,
                                                       (bf16*)d_out, loss_sum, loss_batch, per_sample, B, grad_scale,
                                                       grad_scale_dev);
   VDS_CHECK_LAUNCH("loss");
@@ -156,7 +160,7 @@ int vds_adamw(float* p, const float* g, float* m, float* v, void* p_bf16, const 
   a.gscale = grad_scale;
   a.hyper_dev = hyper_dev;
   a.vec_ok = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)p_bf16 & 7) == 0;
-  adamw_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(a);
+  launch_k(adamw_kernel, n_chunks, 256, 0, (cudaStream_t)stream, a);
   VDS_CHECK_LAUNCH("adamw");
   return VDS_OK;
 }

@@ -265,6 +265,13 @@ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t chunk) {
   return r * 128u + ((chunk ^ (r & 7u)) << 4);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Blocks until every kernel this launch depends on has completed and its writes are visible; before it only
+// launch-independent work (shared memory / TMEM set-up, tensor-map prefetch) is allowed.  No-op without PDL.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the CTAs of the dependent kernel be scheduled as SM resources free up (they then block in their own pdl_wait).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- small math helpers
 // 2^x on the MUFU pipe, one instruction (exp2f() wraps it in a denormal-range fix-up: 3 extra issue slots)
 __device__ __forceinline__ float ex2(float x) {
