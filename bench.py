@@ -7,6 +7,12 @@ N > 1 is launched by torchrun (one rank per GPU, NCCL); the step shards by data-
 scaling: fixed per-rank batch), parameters/gradients are sharded with our own all-gather / reduce-scatter.
 Rank 0 prints ONE JSON line.  `--impl reference` times the reference's CPU eager step (the oracle
 restatement of /root/reference/model.py + train.py, fp32, all host threads) on a bounded sample.
+
+At world size 1 the step is replayed as one CUDA graph (train.GraphedTrainStep; `--eager` issues the kernels from
+Python instead and is also reported as the `eager_issue` extra).  `value` times K steps with the batch resident in
+HBM; `e2e` times K steps that each copy the batch from pinned host memory (vds_b200.data.DevicePrefetcher, copy of
+step i+1 overlapped with step i) and read the loss back; `roofline` is the self-attention backward kernel timed by
+CUDA events around every one of its launches inside the timed steps (event-record nodes when graphed).
 """
 import argparse
 import json
@@ -190,8 +196,13 @@ def run_ours(args):
     latent, noise, context, t = latent_h.to(dev), noise_h.to(dev), context_h.to(dev), t_h.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    # World size 1: the step is captured once and replayed as ONE CUDA graph (train.GraphedTrainStep, the repo's public
+    # API for a launch-bound step); --eager issues the same ~1200 kernels from Python instead.  Multi-GPU runs are
+    # eager (the per-block NCCL collectives are issued from Python).  The dominant kernel is timed live in both modes:
+    # its events are event-record nodes inside the graph (ops.attn_bwd).
     stepper = None
-    if args.graph and world == 1:
+    if world == 1 and not args.eager:
+        ops.PROFILE["attn_bwd_self"] = []
         stepper = train.GraphedTrainStep(model, opt, latent.shape, context.shape, device=dev, warmup=2)
 
     def step(i, lat, ctx):
@@ -212,6 +223,13 @@ def run_ours(args):
     for i in range(args.warmup):
         step(i, latent, context)
     barrier()
+    graph_prof = None
+    if stepper is not None:
+        if stepper.graph is None:            # fewer warm-up steps than the stepper's own eager warm-up: capture now
+            for i in range(3):
+                step(args.warmup + 100 + i, latent, context)
+            barrier()
+        graph_prof = ops.PROFILE.get("attn_bwd_self", [])[-depth:]   # the event nodes recorded during the capture
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -233,6 +251,8 @@ def run_ours(args):
     launches = lib.launch_count() - launches0
     step_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
     prof = ops.PROFILE.pop("attn_bwd_self", [])
+    if graph_prof is not None:
+        prof = graph_prof                    # re-recorded by every replay: these are the last timed step's launches
     kern_ms = sum(a.elapsed_time(b) for a, b in prof) / max(1, len(prof))
     ops.PROFILE.clear()
 
@@ -262,6 +282,27 @@ def run_ours(args):
     sampler.stop_flag = True
 
     # ---- extra (world size 1, eager runs only): the same step replayed from a CUDA graph (train.GraphedTrainStep)
+    eager_ms = None
+    if stepper is not None and not args.no_graph_extra:
+        ev2 = []
+        stepper_saved, stepper = stepper, None
+        hyper_saved, opt.hyper_dev = getattr(opt, "hyper_dev", None), None   # eager steps pass lr / wd by value
+        try:
+            for i in range(2):
+                step(3000 + i, latent, context)
+            barrier()
+            for i in range(args.steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                step(3100 + i, latent, context)
+                e1.record()
+                ev2.append((e0, e1))
+            barrier()
+            eager_ms = sum(a.elapsed_time(b) for a, b in ev2) / args.steps
+        finally:
+            stepper = stepper_saved
+            opt.hyper_dev = hyper_saved
     graph_ms = None
     if world == 1 and stepper is None and not args.no_graph_extra:
         try:
@@ -316,6 +357,9 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss_host},
             "gpu_launches": launches if stepper is None else stepper.launches_per_step * args.steps,
             "cuda_graph": stepper is not None, "clocks": sampler.summary(),
+            "eager_issue": None if eager_ms is None else {
+                "ms_per_step": eager_ms, "value": world * B * N / (eager_ms * 1e-3), "unit": "latent tokens/s",
+                "note": "same step with its kernels issued one by one from Python (no CUDA graph); extra, not the headline"},
             "graph_replay": None if graph_ms is None else {
                 "ms_per_step": graph_ms, "value": world * B * N / (graph_ms * 1e-3), "unit": "latent tokens/s",
                 "note": "same step captured once and replayed as ONE CUDA graph (train.GraphedTrainStep); extra, not the headline"},
@@ -339,7 +383,8 @@ def main():
     ap.add_argument("--workload", default="debug-8k", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="world size 1: capture the whole step in a CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="(default at world size 1) the step is one CUDA graph")
+    ap.add_argument("--eager", action="store_true", help="issue the kernels from Python instead of replaying a graph")
     ap.add_argument("--no-graph-extra", action="store_true", help="skip the extra graph-replay measurement")
     ap.add_argument("--depth", type=int, default=0, help="profiling only: override the model depth (NOT a bench line)")
     args = ap.parse_args()

@@ -270,7 +270,11 @@ def attn_bwd(q, k, v, o, d_o, lse, B, nh, Lq, Lk, dq_acc, dk=None, dv=None, dk_a
     ws = _tail_ws(q.device, B, nh, Lk) if (tail_balance and q_splits == 1) else None
     prof = PROFILE.get("attn_bwd_self") if Lq == Lk else None
     if prof is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # inside a CUDA-graph capture the events become event-record NODES (external=True): every replay re-records
+        # them, so the kernel can be timed live inside a graphed step as well
+        ext = torch.cuda.is_current_stream_capturing()
+        e0 = torch.cuda.Event(enable_timing=True, external=ext)
+        e1 = torch.cuda.Event(enable_timing=True, external=ext)
         e0.record()
     L.check(L.lib().vds_attn_bwd(
         _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(d_o), d_o.stride(0),
