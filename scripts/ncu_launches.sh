@@ -1,9 +1,10 @@
 #!/bin/bash
-# launch list of one bench step (cold-cache, serialised: compare SHARES) -> gpurun_out/launches_$1.csv
+# launch list of one bench step, kernels issued eagerly (--eager: same kernels as the graphed default, countable per step)
+# (cold-cache, serialised: compare SHARES) -> gpurun_out/launches_$1.csv
 TAG=${1:-r1}
 EXTRA=${2:-}
 ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph-extra $EXTRA > gpurun_out/ncu_bench_$TAG.log 2>&1
+    python bench.py --eager --steps 1 --warmup 3 --no-cpu-baseline --no-graph-extra $EXTRA > gpurun_out/ncu_bench_$TAG.log 2>&1
 python - <<PY
 import csv, collections, sys
 rows = list(csv.reader(open("gpurun_out/launches_$TAG.csv", errors="ignore")))
