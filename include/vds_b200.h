@@ -48,7 +48,11 @@ enum vds_gemm_epilogue {
   VDS_EPI_BIAS_GELU = 2, /* C = bf16(acc+bias) ; C2 = bf16(gelu_erf(C))        model.py:84-85    */
   VDS_EPI_GATE_RES = 3,  /* C = bf16(acc+bias?) ; C2 = bf16(aux + bf16(C*gate[b]))  model.py:139 */
   VDS_EPI_DGELU = 4,     /* C = bf16(acc * gelu'(aux))                                          */
-  VDS_EPI_STORE_F32 = 5  /* C(fp32) = acc + bias?                                               */
+  VDS_EPI_STORE_F32 = 5, /* C(fp32) = acc + bias?                                               */
+  VDS_EPI_STORE_ROWDOT = 6 /* C = bf16(acc) ; rowdot[(b*(N/128) + n/128) * rows_per_batch + r] += sum over the 128-column
+                            * head of C*aux (fp32; C2 = float* rowdot, zero-initialised by the caller): the dgrad GEMM
+                            * that produces dO also emits delta = rowsum(dO*O) of the attention backward
+                            * (model.py:136 backward).  2-CTA tile path only: VDS_ERR_UNSUPPORTED otherwise. */
 };
 
 typedef struct vds_gemm_args {

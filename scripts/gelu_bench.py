@@ -20,3 +20,8 @@ o1 = torch.empty((M, 4*h), device="cuda").bfloat16(); o2 = torch.empty_like(o1)
 mn, _ = timeit(lambda: (ops.gemm(a, w1, bias=b1, out=o1), ops.gemm(a, w1, bias=b1, out=o2))); print("two plain GEMMs", mn*1e3, "us")
 mn, _ = timeit(lambda: ops.gemm(a, w1, bias=b1, tile_n=128, cluster=1)); print("plain 1-CTA BN=128", mn*1e3, "us")
 mn, _ = timeit(lambda: ops.gemm(a, w1, bias=b1, cluster=1)); print("plain 1-CTA BN=256", mn*1e3, "us")
+# dgrad of attn_proj (N = K = 512) with / without the fused delta = rowsum(dO * O)
+wp = (torch.randn((h, h), device="cuda")*0.05).bfloat16(); oo = torch.randn((M, h), device="cuda").bfloat16()
+delta = torch.zeros((2, 4, 8208), device="cuda", dtype=torch.float32)
+mn, _ = timeit(lambda: ops.gemm(dy, wp, b_mn=True)); print("dgrad proj plain", mn*1e3, "us")
+mn, _ = timeit(lambda: ops.gemm_dgrad_rowdot(dy, wp, oo, delta, 8208)); print("dgrad proj + rowdot epilogue", mn*1e3, "us")

@@ -138,3 +138,25 @@ def test_gemm_cluster_multicast_matches(cuda_dev, M, N, K, cluster):
     out = torch.zeros((M, N), device=cuda_dev, dtype=torch.float32)
     ops.gemm(g1, g2, a_mn=True, b_mn=True, epilogue=lib.EPI_ACCUM_F32, out=out, splits=2, cluster=cluster)
     _close(out, g1.float().t() @ g2.float())
+
+
+def test_dgrad_rowdot_epilogue_matches_separate_kernels(cuda_dev):
+    """VDS_EPI_STORE_ROWDOT: the dgrad GEMM that produces dO also emits delta[b, head, r] = <dO_head, O_head>
+    (what attn_bwd_prep computes from the stored bf16 dO).  dX must be bit-identical to the plain GEMM."""
+    from vds_b200 import ops
+    torch.manual_seed(0)
+    B, L, h, nh = 2, 8208, 512, 4
+    M = B * L
+    dy = torch.randn((M, h), device=cuda_dev).bfloat16()
+    w = (torch.randn((h, h), device=cuda_dev) * 0.05).bfloat16()
+    o = torch.randn((M, h), device=cuda_dev).bfloat16()
+    ref_dx = ops.gemm(dy, w, b_mn=True)
+    delta = torch.zeros((B, nh, L), device=cuda_dev, dtype=torch.float32)
+    dx = ops.gemm_dgrad_rowdot(dy, w, o, delta, L)
+    assert dx is not None, "2-CTA path expected for this shape"
+    assert torch.equal(dx, ref_dx)
+    ref_delta = (ref_dx.float() * o.float()).view(B, L, nh, 128).sum(-1).permute(0, 2, 1)
+    assert torch.allclose(delta, ref_delta, rtol=1e-4, atol=1e-3), (delta - ref_delta).abs().max().item()
+    # shapes without a 2-CTA tile path report "unsupported" (None) instead of computing something else
+    small = ops.gemm_dgrad_rowdot(dy[:256], w, o[:256], torch.zeros((1, nh, 256), device=cuda_dev), 256)
+    assert small is None

@@ -844,7 +844,7 @@ int64_t vds_attn_bwd_tail_ws_bytes(int B, int nh, int Lk) {
   return (int64_t)(num_sms() - 1) * 2 * 128 * HD * 4;   // at most SMs-1 remainder items
 }
 
-/* delta = rowsum(dO * O); dq_acc must be zero-initialised fp32 [B, Lq, lddq]; with q_splits > 1 dk/dv are
+/* delta = rowsum(dO * O) (computed here from o, or passed in precomputed when o == NULL); dq_acc must be zero-initialised fp32 [B, Lq, lddq]; with q_splits > 1 dk/dv are
  * accumulated into zero-initialised fp32 buffers dk_acc/dv_acc [B, Lk, ldkv_acc] instead of dk/dv. */
 int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
                  int64_t ldo, const void* d_o, int64_t lddo, const float* lse, float* delta, float* dq_acc,
@@ -868,7 +868,7 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
     if (e != cudaSuccess) { set_error("attn_bwd: smem attribute: %s", cudaGetErrorString(e)); return VDS_ERR_CUDA; }
     attr = true;
   }
-  {
+  if (o != nullptr) {   // o == NULL: delta was produced by the dgrad GEMM's STORE_ROWDOT epilogue
     const long long warps = (long long)B * Lq * nh;
     launch_k(attn_bwd_prep_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream, 
         (const bf16*)o, (const bf16*)d_o, ldo, lddo, delta, B, Lq, nh);

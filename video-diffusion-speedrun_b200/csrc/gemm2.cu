@@ -31,7 +31,8 @@ constexpr int G2_MAX_STAGES = 6;
 // operand prefetched by TMA one group ahead / both outputs stored without waiting in between).
 template <int EPI>
 struct G2Cfg {
-  static constexpr bool fused = EPI == VDS_EPI_BIAS_GELU || EPI == VDS_EPI_GATE_RES || EPI == VDS_EPI_DGELU;
+  static constexpr bool fused = EPI == VDS_EPI_BIAS_GELU || EPI == VDS_EPI_GATE_RES || EPI == VDS_EPI_DGELU ||
+                                EPI == VDS_EPI_STORE_ROWDOT;
   static constexpr int stages = fused ? 5 : 6;
   static constexpr int stg_warp = fused ? 8192 : 4096;
 };
@@ -92,7 +93,7 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
                                                     uint32_t tmem_base, uint32_t tfull_bar0, uint32_t leader_tempty0,
                                                     int tile0, int tile_step, int total_tiles, int m_pairs, int n_tiles,
                                                     int crank, int q, int chalf, int lane) {
-  constexpr bool kAux = (EPI == VDS_EPI_GATE_RES || EPI == VDS_EPI_DGELU);
+  constexpr bool kAux = (EPI == VDS_EPI_GATE_RES || EPI == VDS_EPI_DGELU || EPI == VDS_EPI_STORE_ROWDOT);
   uint8_t* S1 = S0 + 4096;
   const uint32_t s0 = smem_u32(S0), s1 = smem_u32(S1);
   auto row_of = [&](int tile) { return ((tile % m_pairs) * 2 + crank) * BM + q * 32; };
@@ -102,7 +103,7 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
     mbar_expect_tx(aux_bar, 4096);
     tma_load_2d(s1, tmAux, aux_bar, col_of(tile0, 0), row_of(tile0));
   }
-  const bool has_bias = (EPI != VDS_EPI_DGELU) && p.bias != nullptr;
+  const bool has_bias = (EPI != VDS_EPI_DGELU && EPI != VDS_EPI_STORE_ROWDOT) && p.bias != nullptr;
   const bool trace = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
   long long c_tf = 0, c_ld = 0, c_aux = 0, c_math = 0, c_rd = 0, c_sts = 0, c_st = 0;
   int it = 0;
@@ -148,6 +149,7 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
       c_aux += clock64() - tq;
       tq = clock64();
       uint4 keep[8];    // second output (bf16 Linear result)
+      float dot = 0.f;  // STORE_ROWDOT: this row's partial <C, aux> over the 64 columns of the group
       const int b = (EPI == VDS_EPI_GATE_RES) ? min(row0 + lane, p.M - 1) / p.rows_per_batch : 0;
       uint4 bnext = make_uint4(0u, 0u, 0u, 0u), gnext = make_uint4(0u, 0u, 0u, 0u);
       if (has_bias) bnext = __ldg(reinterpret_cast<const uint4*>(p.bias + col0));
@@ -188,6 +190,13 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
 #pragma unroll
           for (int j = 0; j < 8; ++j) o8[j] = x8[j] + bf16_round(a8[j] * g8[j]);   // x + (out * gate), each op rounded
           outv = pack8(o8);
+        } else if constexpr (EPI == VDS_EPI_STORE_ROWDOT) {
+          float x8[8];
+          unpack8(xa[g], x8);
+          outv = pack8(a8);
+          unpack8(outv, a8);                                  // the consumer (attention backward) sees the bf16 values
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dot = fmaf(a8[j], x8[j], dot);
         } else {   // DGELU
           float h8[8];
           unpack8(xa[g], h8);
@@ -210,8 +219,16 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
       __syncwarp();
       c_sts += clock64() - tq;
       tq = clock64();
+      if constexpr (EPI == VDS_EPI_STORE_ROWDOT) {
+        const int row = row0 + lane;
+        if (row < p.M) {
+          const int bb = row / p.rows_per_batch, rr = row % p.rows_per_batch;
+          float* dst = reinterpret_cast<float*>(p.C2) + ((long long)bb * (p.N >> 7) + (col0 >> 7)) * p.rows_per_batch + rr;
+          atomicAdd(dst, dot);   // two 64-column groups per head: a two-term sum, order-independent
+        }
+      }
       if (lane == 0) {
-        if constexpr (EPI == VDS_EPI_DGELU) {
+        if constexpr (EPI == VDS_EPI_DGELU || EPI == VDS_EPI_STORE_ROWDOT) {
           tma_store_2d(tmC, s0, col0, row0);
         } else {
           tma_store_2d(tmC2, s0, col0, row0);
@@ -420,7 +437,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
-      } else {
+      } else if constexpr (EPI != VDS_EPI_STORE_ROWDOT) {   // (ROWDOT exists only as the fused fast path)
         uint8_t* stg = smem_gen + G2_STAGES * G2_STAGE + (warp - 2) * 4096;   // 1024-byte aligned (TMA swizzle atom)
         constexpr int GROUPS = G2_BN / 128;
 #pragma unroll 1
@@ -503,7 +520,7 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
       return encode_tmap_bf16(tm, ptr, 2, dims, strides, box);
     };
     const bool need_aux = EPI != VDS_EPI_BIAS_GELU;
-    const bool main_c2 = EPI != VDS_EPI_DGELU;   // primary output is C2 (act / residual stream), C for dGELU
+    const bool main_c2 = EPI != VDS_EPI_DGELU && EPI != VDS_EPI_STORE_ROWDOT;   // primary output: C2 (act / residual stream), else C
     bool good = main_c2 ? ok(a.C2, a.ldc2) : ok(a.C, a.ldc);
     if (main_c2 && a.C != nullptr) good = good && ok(a.C, a.ldc);
     if (need_aux) good = good && ok(a.aux, a.ldaux);
@@ -514,6 +531,12 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
       if (!r && need_aux) r = enc(&tmAux, a.aux, a.ldaux);
       if (r) return r;
       fast = 1;
+    }
+  }
+  if (EPI == VDS_EPI_STORE_ROWDOT) {
+    if (!fast || a.C2 == nullptr || a.rows_per_batch <= 0 || a.N % 128 != 0) {
+      set_error("gemm2: STORE_ROWDOT needs TMA-able C / aux, a rowdot buffer (C2), rows_per_batch and N %% 128 == 0");
+      return VDS_ERR_UNSUPPORTED;
     }
   }
   GemmDev p;
@@ -584,6 +607,7 @@ int gemm2_dispatch(const vds_gemm_args& a, cudaStream_t s) {
     switch (a.epilogue) {
       case VDS_EPI_STORE: return launch_gemm2<false, true, VDS_EPI_STORE>(a, s);
       case VDS_EPI_DGELU: return launch_gemm2<false, true, VDS_EPI_DGELU>(a, s);
+      case VDS_EPI_STORE_ROWDOT: return launch_gemm2<false, true, VDS_EPI_STORE_ROWDOT>(a, s);
       default: return VDS_ERR_UNSUPPORTED;
     }
   }

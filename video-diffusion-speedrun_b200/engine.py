@@ -284,18 +284,21 @@ def backward(model, P, c, dout, sink):
             Lc = c.Lc
             do2 = ops.gate_bwd(dX2, s.o2, gate_ca, dm[5], B, Lr, h)
             sink.wgrad(pre + "cross_proj.weight", do2, s.ca)
-            dca = ops.gemm(do2, P[pre + "cross_proj.weight"], b_mn=True)
+            delta2 = torch.zeros((B, nh, Lr), **f32)
+            dca = ops.gemm_dgrad_rowdot(do2, P[pre + "cross_proj.weight"], s.ca, delta2, Lr)
+            if dca is None:
+                dca, delta2 = ops.gemm(do2, P[pre + "cross_proj.weight"], b_mn=True), None
             dq_acc = torch.zeros((B * Lr, h), **f32)
             qs = _attn_q_splits((Lc + 127) // 128, B, nh, (Lr + 127) // 128)
             if qs > 1:
                 dckv_f = torch.zeros((B * Lc, 2 * h), **f32)
                 ops.attn_bwd(s.qc, s.ckv[:, :h], s.ckv[:, h:], s.ca, dca, s.lse2, B, nh, Lr, Lc, dq_acc,
-                             dk_acc=dckv_f[:, :h], dv_acc=dckv_f[:, h:], q_splits=qs)
+                             dk_acc=dckv_f[:, :h], dv_acc=dckv_f[:, h:], q_splits=qs, delta=delta2)
                 dckv = ops.cast_f32_bf16(dckv_f)
             else:
                 dckv = torch.empty((B * Lc, 2 * h), device=dev, dtype=torch.bfloat16)
                 ops.attn_bwd(s.qc, s.ckv[:, :h], s.ckv[:, h:], s.ca, dca, s.lse2, B, nh, Lr, Lc, dq_acc,
-                             dk=dckv[:, :h], dv=dckv[:, h:])
+                             dk=dckv[:, :h], dv=dckv[:, h:], delta=delta2)
             dqc = ops.cast_f32_bf16(dq_acc)
             sink.wgrad(pre + "context_kv.weight", dckv, c.ctx2d)
             sink.bgrad(pre + "context_kv.bias", dckv)
@@ -311,11 +314,14 @@ def backward(model, P, c, dout, sink):
         # ---- self-attention branch
         do1 = ops.gate_bwd(dX1, s.o1, gate_sa, dm[2], B, Lr, h)
         sink.wgrad(pre + "attn_proj.weight", do1, s.a)
-        da = ops.gemm(do1, P[pre + "attn_proj.weight"], b_mn=True)
+        delta1 = torch.zeros((B, nh, Lr), **f32)
+        da = ops.gemm_dgrad_rowdot(do1, P[pre + "attn_proj.weight"], s.a, delta1, Lr)   # dO and delta = rowsum(dO * O)
+        if da is None:
+            da, delta1 = ops.gemm(do1, P[pre + "attn_proj.weight"], b_mn=True), None
         dqkv = torch.empty((B * Lr, 3 * h), device=dev, dtype=torch.bfloat16)
         dq_acc = torch.zeros((B * Lr, h), **f32)
         ops.attn_bwd(s.qkv[:, :h], s.qkv[:, h:2 * h], s.V, s.a, da, s.lse, B, nh, Lr, Lr, dq_acc, dk=dqkv[:, h:2 * h],
-                     dv=dqkv[:, 2 * h:])
+                     dv=dqkv[:, 2 * h:], delta=delta1)
         if s.use_mix:
             mode = 1
         elif i == 0 and dv0_acc is not None:

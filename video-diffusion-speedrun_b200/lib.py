@@ -42,7 +42,8 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
-EPI_STORE, EPI_ACCUM_F32, EPI_BIAS_GELU, EPI_GATE_RES, EPI_DGELU, EPI_STORE_F32 = range(6)
+ERR_UNSUPPORTED = -3
+EPI_STORE, EPI_ACCUM_F32, EPI_BIAS_GELU, EPI_GATE_RES, EPI_DGELU, EPI_STORE_F32, EPI_STORE_ROWDOT = range(7)
 
 fp = ctypes.POINTER(ctypes.c_float)
 

@@ -87,8 +87,22 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=L.EPI_STORE, out=None, out2=N
     args.cluster = cluster
     if remap is not None:
         args.remap_rows, args.remap_stride, args.remap_offset = remap
-    L.check(L.lib().vds_gemm(ctypes.byref(args), _stream()), "vds_gemm")
+    rc = L.lib().vds_gemm(ctypes.byref(args), _stream())
+    if rc == L.ERR_UNSUPPORTED and epilogue == L.EPI_STORE_ROWDOT:
+        return None                      # caller falls back to the plain GEMM + separate row-dot kernel
+    L.check(rc, "vds_gemm")
+    if epilogue == L.EPI_STORE_ROWDOT:
+        return out
     return (out, out2) if out2 is not None else out
+
+
+def gemm_dgrad_rowdot(dy, w, o, rowdot, rows_per_batch):
+    """dX = dy @ W (dgrad, W [N_out, N_in] read MN-major) and, in the same epilogue, rowdot[b, head, r] += <dX_head, o_head>
+    per 128-column head — the `delta` of the attention backward.  `rowdot`: zero-initialised fp32 [B, N_in/128,
+    rows_per_batch].  Returns dX, or None when the shape has no 2-CTA tile path (the caller then runs the plain
+    GEMM and lets vds_attn_bwd compute delta itself)."""
+    assert rowdot.dtype == torch.float32 and rowdot.is_contiguous()
+    return gemm(dy, w, b_mn=True, epilogue=L.EPI_STORE_ROWDOT, aux=o, out2=rowdot, rows_per_batch=rows_per_batch)
 
 
 def _p(t):
@@ -263,10 +277,15 @@ def _tail_ws(device, B, nh, Lk):
 
 
 def attn_bwd(q, k, v, o, d_o, lse, B, nh, Lq, Lk, dq_acc, dk=None, dv=None, dk_acc=None, dv_acc=None, q_splits=1,
-             hd=128, tail_balance=True):
-    """dq_acc: zeroed fp32 [B*Lq, nh*hd]; dk/dv: bf16 2-D views (q_splits == 1) or fp32 accumulators."""
+             hd=128, tail_balance=True, delta=None):
+    """dq_acc: zeroed fp32 [B*Lq, nh*hd]; dk/dv: bf16 2-D views (q_splits == 1) or fp32 accumulators.
+    delta: precomputed rowsum(dO * O) fp32 [B, nh, Lq] (gemm_dgrad_rowdot); None -> computed here from o and d_o."""
     _chk_bf16(q, k, v, o, d_o)
-    delta = torch.empty((B, nh, Lq), device=q.device, dtype=torch.float32)
+    have_delta = delta is not None
+    if not have_delta:
+        delta = torch.empty((B, nh, Lq), device=q.device, dtype=torch.float32)
+    else:
+        assert delta.dtype == torch.float32 and delta.is_contiguous() and delta.numel() == B * nh * Lq
     ws = _tail_ws(q.device, B, nh, Lk) if (tail_balance and q_splits == 1) else None
     prof = PROFILE.get("attn_bwd_self") if Lq == Lk else None
     if prof is not None:
@@ -277,7 +296,8 @@ def attn_bwd(q, k, v, o, d_o, lse, B, nh, Lq, Lk, dq_acc, dk=None, dv=None, dk_a
         e1 = torch.cuda.Event(enable_timing=True, external=ext)
         e0.record()
     L.check(L.lib().vds_attn_bwd(
-        _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(o), o.stride(0), _p(d_o), d_o.stride(0),
+        _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), None if have_delta else _p(o), o.stride(0), _p(d_o),
+        d_o.stride(0),
         _p(lse), _p(delta), _p(dq_acc), dq_acc.stride(0), _p(dk), dk.stride(0) if dk is not None else 0, _p(dv),
         dv.stride(0) if dv is not None else 0, _p(dk_acc), _p(dv_acc),
         dk_acc.stride(0) if dk_acc is not None else 0, q_splits, B, nh, Lq, Lk, hd, float(hd) ** -0.5,
