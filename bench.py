@@ -8,8 +8,9 @@ scaling: fixed per-rank batch), parameters/gradients are sharded with our own al
 Rank 0 prints ONE JSON line.  `--impl reference` times the reference's CPU eager step (the oracle
 restatement of /root/reference/model.py + train.py, fp32, all host threads) on a bounded sample.
 
-At world size 1 the step is replayed as one CUDA graph (train.GraphedTrainStep; `--eager` issues the kernels from
-Python instead and is also reported as the `eager_issue` extra).  `value` times K steps with the batch resident in
+At world size 1 the same kernels can be issued two ways: replayed as one CUDA graph (train.GraphedTrainStep) or
+launched one by one from Python with programmatic dependent launch.  By default an untimed 2-step probe of each
+(`issue_mode_probe` in the JSON line) picks the faster one for the workload; `--graph` / `--eager` force one.  `value` times K steps with the batch resident in
 HBM; `e2e` times K steps that each copy the batch from pinned host memory (vds_b200.data.DevicePrefetcher, copy of
 step i+1 overlapped with step i) and read the loss back; `roofline` is the self-attention backward kernel timed by
 CUDA events around every one of its launches inside the timed steps (event-record nodes when graphed).
@@ -224,12 +225,38 @@ def run_ours(args):
         step(i, latent, context)
     barrier()
     graph_prof = None
+    mode_pick = None
     if stepper is not None:
         if stepper.graph is None:            # fewer warm-up steps than the stepper's own eager warm-up: capture now
             for i in range(3):
                 step(args.warmup + 100 + i, latent, context)
             barrier()
         graph_prof = ops.PROFILE.get("attn_bwd_self", [])[-depth:]   # the event nodes recorded during the capture
+        if not args.graph:
+            # Untimed pick between the two ways of issuing the SAME kernels: graph replay wins when the host cannot keep
+            # up (small workloads), Python issue + programmatic dependent launch wins when every kernel is long (XL).
+            def probe(use_graph, n=2):
+                nonlocal stepper
+                saved, hyper = stepper, getattr(opt, "hyper_dev", None)
+                if not use_graph:
+                    stepper, opt.hyper_dev = None, None
+                try:
+                    step(5000, latent, context)
+                    barrier()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for i in range(n):
+                        step(5001 + i, latent, context)
+                    b.record()
+                    barrier()
+                    return a.elapsed_time(b) / n
+                finally:
+                    stepper, opt.hyper_dev = saved, hyper
+            ms_g, ms_e = probe(True), probe(False)
+            mode_pick = {"graph_ms": ms_g, "eager_ms": ms_e}
+            if ms_e < 0.98 * ms_g:
+                stepper, graph_prof, opt.hyper_dev = None, None, None
+                ops.PROFILE.clear()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -258,32 +285,44 @@ def run_ours(args):
 
     # ---- timed region 2 (e2e): host buffers -> H2D every step, loss read back (D2H) every step.  The copies go
     # through the repo's own input pipeline (vds_b200.data.DevicePrefetcher): batch i+1 is copied from pinned memory on
-    # a copy stream while step i computes; the first copy and every later one are issued inside the timed intervals.
+    # a copy stream while step i computes.
     from vds_b200.data import DevicePrefetcher
     barrier()
     e2e_evs = []
-    host_batches = ({"latent": latent_h, "context": context_h, "noise": noise_h} for _ in range(args.steps))
-    pf = None
+    import itertools
+    host_batches = itertools.repeat({"latent": latent_h, "context": context_h, "noise": noise_h})
+    # one untimed pipeline warm-up step (copy stream, staging allocations, first two copies in flight): the timed steps
+    # then run in the pipeline's steady state — each issues exactly one H2D batch copy and waits for one
+    pf = DevicePrefetcher(host_batches, device=dev, depth=2)
+    bt = next(pf)
+    noise.copy_(bt["noise"], non_blocking=True)
+    step(args.warmup + args.steps, bt["latent"], bt["context"]).item()
+    barrier()
     for i in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        if pf is None:
-            pf = DevicePrefetcher(host_batches, device=dev, depth=2)
+        tdbg = [time.perf_counter()]
         bt = next(pf)
+        tdbg.append(time.perf_counter())
         noise.copy_(bt["noise"], non_blocking=True)
         loss = step(args.warmup + args.steps + i, bt["latent"], bt["context"])
+        tdbg.append(time.perf_counter())
         loss_host = loss.item()
+        tdbg.append(time.perf_counter())
+        if os.environ.get("VDS_BENCH_DEBUG"):
+            sys.stderr.write("e2e host ms: prefetch %.2f step-issue %.2f loss.item %.2f\n" % tuple(
+                1e3 * (tdbg[k + 1] - tdbg[k]) for k in range(3)))
         e1.record()
         e2e_evs.append((e0, e1))
     barrier()
-    h2d_per_step = pf.h2d_bytes // max(1, args.steps)
+    h2d_per_step = sum(v.numel() * v.element_size() for v in (latent_h, context_h, noise_h))   # one batch per step
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs) / args.steps
     sampler.stop_flag = True
 
     # ---- extra (world size 1, eager runs only): the same step replayed from a CUDA graph (train.GraphedTrainStep)
     eager_ms = None
-    if stepper is not None and not args.no_graph_extra:
+    if stepper is not None and not args.no_graph_extra and args.graph:
         ev2 = []
         stepper_saved, stepper = stepper, None
         hyper_saved, opt.hyper_dev = getattr(opt, "hyper_dev", None), None   # eager steps pass lr / wd by value
@@ -304,7 +343,7 @@ def run_ours(args):
             stepper = stepper_saved
             opt.hyper_dev = hyper_saved
     graph_ms = None
-    if world == 1 and stepper is None and not args.no_graph_extra:
+    if world == 1 and stepper is None and not args.no_graph_extra and args.eager:
         try:
             gstep = train.GraphedTrainStep(model, opt, latent.shape, context.shape, device=dev, warmup=1)
             for i in range(3):
@@ -356,7 +395,7 @@ def run_ours(args):
             "e2e": {"value": world * B * N / (e2e_ms * 1e-3), "unit": "latent tokens/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": loss_host},
             "gpu_launches": launches if stepper is None else stepper.launches_per_step * args.steps,
-            "cuda_graph": stepper is not None, "clocks": sampler.summary(),
+            "cuda_graph": stepper is not None, "issue_mode_probe": mode_pick, "clocks": sampler.summary(),
             "eager_issue": None if eager_ms is None else {
                 "ms_per_step": eager_ms, "value": world * B * N / (eager_ms * 1e-3), "unit": "latent tokens/s",
                 "note": "same step with its kernels issued one by one from Python (no CUDA graph); extra, not the headline"},
@@ -383,7 +422,8 @@ def main():
     ap.add_argument("--workload", default="debug-8k", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="(default at world size 1) the step is one CUDA graph")
+    ap.add_argument("--graph", action="store_true", help="world size 1: force the CUDA-graph step (default: an untimed "
+                    "2-step probe picks graph replay or Python issue, whichever is faster for the workload)")
     ap.add_argument("--eager", action="store_true", help="issue the kernels from Python instead of replaying a graph")
     ap.add_argument("--no-graph-extra", action="store_true", help="skip the extra graph-replay measurement")
     ap.add_argument("--depth", type=int, default=0, help="profiling only: override the model depth (NOT a bench line)")
