@@ -119,18 +119,13 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
 #pragma unroll 1
     for (int gi = 0; gi < 2; ++gi) {
       const int col0 = col_of(tile, gi);
-      uint32_t r0[32], r1[32];
+      // accumulator columns are read 16 at a time, one load ahead of the math (a full 64-column read up front keeps 64
+      // registers live through the whole group and pushes ptxas into a serial, latency-exposed schedule)
+      uint32_t ra[16], rb[16];
       tq = clock64();
-      tmem_ld32(t_base + (chalf * 2 + gi) * 64, r0);
-      tmem_ld32(t_base + (chalf * 2 + gi) * 64 + 32, r1);
-      tmem_ld_wait();
+      tmem_ld16(t_base + (chalf * 2 + gi) * 64, ra);
       c_ld += clock64() - tq;
       tq = clock64();
-      if (gi == 1) {   // accumulator buffer drained: the MMA warp may start the tile after next
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
-      }
       uint4 xa[8];      // aux row of this thread
       if constexpr (kAux) {
         mbar_wait(aux_bar, aux_phase);
@@ -165,9 +160,21 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
         }
         uint4 outv;
         float a8[8];
+        if ((g & 1) == 0) {
+          tmem_ld_wait();
+          if (g < 6) {
+            tmem_ld16(t_base + (chalf * 2 + gi) * 64 + (g + 2) * 8, (g & 2) ? ra : rb);
+          } else if (gi == 1) {   // last read of this accumulator buffer is complete: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
+          }
+        }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a8[j] = __uint_as_float(g < 4 ? r0[g * 8 + j] : r1[(g - 4) * 8 + j]);
-        if (has_bias) {
+        for (int j = 0; j < 8; ++j) a8[j] = __uint_as_float(((g & 2) ? rb : ra)[(g & 1) * 8 + j]);
+        if constexpr (EPI == VDS_EPI_BIAS_GELU || EPI == VDS_EPI_GATE_RES) {
+          // unconditional (braw is zero without a bias): a branch here would cut the group into one basic block per
+          // chunk and ptxas schedules only inside basic blocks
           float bb[8];
           unpack8(braw, bb);
 #pragma unroll
