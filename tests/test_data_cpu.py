@@ -36,3 +36,17 @@ def test_prefetcher_refuses_cpu():
     from vds_b200.data import DevicePrefetcher
     with pytest.raises(RuntimeError):
         DevicePrefetcher([], device="cpu")
+
+
+def test_attention_backward_query_split_model():
+    """engine._attn_q_splits: pure host logic choosing how many ways the query range of an attention backward is split
+    when there are fewer (kv tile, head, batch) items than SMs (cross-attention, Lk = 512)."""
+    from vds_b200.engine import _attn_q_splits as qs
+    assert qs(65, 2, 4, 65) == 1                      # self-attention at L = 8208: 520 items >= 148 SMs, never split
+    s = qs(4, 2, 4, 65)                               # cross-attention of the debug model: 32 items
+    assert 2 <= s <= 9 and (32 * s + 147) // 148 <= 2   # at most two waves (was 10 splits = 3 waves)
+    for items in (1, 8, 32, 100, 147):
+        for nq in (1, 3, 17, 65):
+            v = qs(items, 1, 1, nq)
+            assert 1 <= v <= max(1, 2 * nq)           # never more splits than 64-row sub-tiles
+    assert qs(1, 1, 1, 1) <= 2
