@@ -105,6 +105,14 @@ def _worker(rank, world, port, out):
         # 5. get_mup_setup works on the sharded module (full shapes from paramstatus)
         groups, settings = m.get_mup_setup(1e-3, 1e-1, ["patch_proj", "context_kv", "positional_embedding"])
         assert sum(len(g["params"]) for g in groups) == len(names)
+        # 6. sharded save in the reference layout (all ranks call, DCP de-duplicates) and reload on rank 0
+        from vds_b200.checkpoint import read_checkpoint, save_checkpoint
+        ck = os.path.join(os.environ["VDS_TEST_TMP"], "ck")
+        save_checkpoint(m, ck, skip_rope=True)
+        plain = read_checkpoint(ck)
+        for n in names:
+            assert torch.equal(plain[n], ref[n]), n
+        assert "rope.freqs_hwt_cos" not in plain
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
@@ -113,8 +121,9 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_world2_gloo_allgather_reducescatter_statedict():
+def test_world2_gloo_allgather_reducescatter_statedict(tmp_path):
     world = 2
+    os.environ["VDS_TEST_TMP"] = str(tmp_path)
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
