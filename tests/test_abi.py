@@ -46,3 +46,20 @@ def test_no_cpu_fallback():
     m = DiT(in_channels=16, hidden_size=256, depth=1, num_heads=2, cross_attn_input_size=64)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 16, 2, 4, 4), torch.zeros(1, 8, 64), torch.tensor([0.5]))
+
+
+def test_epilogue_enum_matches_header():
+    """The Python constants of the GEMM epilogues are the header's enum values (a silent mismatch would select the
+    wrong fused epilogue)."""
+    import os
+    import re
+
+    import vds_b200  # noqa: F401
+    from vds_b200 import lib
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "vds_b200.h")).read()
+    enum = dict(re.findall(r"(VDS_EPI_[A-Z0-9_]+) = (\d+)", hdr))
+    assert len(enum) == 7
+    for name, val in enum.items():
+        assert getattr(lib, name.replace("VDS_", "")) == int(val), name
+    err = dict(re.findall(r"(VDS_ERR_[A-Z]+) = (-\d+)", hdr))
+    assert lib.ERR_UNSUPPORTED == int(err["VDS_ERR_UNSUPPORTED"])
