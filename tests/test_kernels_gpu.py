@@ -286,6 +286,90 @@ def test_attn_fwd_bwd(cuda_dev, B, nh, Lq, Lk):
         _close(dv, rdv, tol=3e-2, name="dv")
 
 
+def test_attn_growing_max_takes_the_rescale_path(cuda_dev):
+    """The forward exponentiates a tile against the running max of the previous tiles and redoes it exactly when some
+    row's max grew by more than 2^8.  Unit-scale random inputs never trigger that, so this case makes the scores of
+    later key tiles much larger (keys scaled up with position) and checks forward, LSE and backward against fp32 SDPA."""
+    from vds_b200 import ops
+    B, nh, L, hd = 1, 2, 1040, 128          # 9 key tiles, last one ragged
+    h = nh * hd
+    g = torch.Generator(device="cpu").manual_seed(40)
+    q = torch.randn((B * L, h), generator=g)
+    k = torch.randn((B * L, h), generator=g)
+    ramp = torch.linspace(0.5, 6.0, L).repeat(B).unsqueeze(1)     # |scores| grow ~12x from the first to the last tile
+    k = k * ramp
+    v = torch.randn((B * L, h), generator=g)
+    q2, k2, v2 = (t.bfloat16().to(cuda_dev) for t in (q, k, v))
+    out, lse = ops.attn_fwd(q2, k2, v2, B, nh, L, L)
+    qf = rearrange(q2.reshape(B, L, nh, hd), "b l h d -> b h l d").float().requires_grad_(True)
+    kf = rearrange(k2.reshape(B, L, nh, hd), "b l h d -> b h l d").float().requires_grad_(True)
+    vf = rearrange(v2.reshape(B, L, nh, hd), "b l h d -> b h l d").float().requires_grad_(True)
+    s = (qf @ kf.transpose(-1, -2)) * hd ** -0.5
+    # the premise of the test: row maxima really jump by more than 8 (log2 domain) between early and late tiles
+    m_first = (s[..., :128].max(-1).values * 1.4426950408889634)
+    m_all = (s.max(-1).values * 1.4426950408889634)
+    assert ((m_all - m_first) > 8.0).float().mean().item() > 0.5
+    ref = _ref_attn(qf, kf, vf)
+    _close(out, rearrange(ref, "b h l d -> (b l) (h d)"), tol=2e-2, name="attn out (rescale path)")
+    _close(lse, (torch.logsumexp(s, -1) * 1.4426950408889634).detach(), tol=1e-3, name="lse (rescale path)")
+    d_o = _r((B * L, h), cuda_dev, 41)
+    ref.backward(rearrange(d_o.float().view(B, L, nh, hd), "b l h d -> b h l d"))
+    dq_acc = torch.zeros((B * L, h), device=cuda_dev, dtype=torch.float32)
+    dk = torch.zeros((B * L, h), device=cuda_dev, dtype=torch.bfloat16)
+    dv = torch.zeros_like(dk)
+    ops.attn_bwd(q2, k2, v2, out, d_o, lse, B, nh, L, L, dq_acc, dk=dk, dv=dv)
+    for got, want, name in ((dq_acc, qf.grad, "dq"), (dk, kf.grad, "dk"), (dv, vf.grad, "dv")):
+        want = rearrange(want, "b h l d -> (b l) (h d)")
+        assert _cos(got, want) > 0.999, (name, _cos(got, want))
+
+
+def test_attn_full_size_properties(cuda_dev):
+    """S_dbg size (B=2, 4 heads, L=8208, what bench.py runs): size-independent properties instead of a dense reference.
+    (i) rows of softmax sum to one: with V = ones the output is exactly 1 and dV = column sums of P = sum of dO weights;
+    (ii) linearity in V and dO; (iii) a spot check of 64 query rows per (b, head) against fp32 SDPA on those rows."""
+    from vds_b200 import ops
+    B, nh, L, hd = 2, 4, 8208, 128
+    h = nh * hd
+    qkv = _r((B * L, 3 * h), cuda_dev, 50)
+    q2, k2, v2 = qkv[:, :h], qkv[:, h:2 * h], qkv[:, 2 * h:]
+    ones = torch.ones((B * L, h), device=cuda_dev, dtype=torch.bfloat16)
+    out1, lse = ops.attn_fwd(q2, k2, ones, B, nh, L, L)
+    assert (out1.float() - 1.0).abs().max().item() < 1e-2
+    out, lse2 = ops.attn_fwd(q2, k2, v2, B, nh, L, L)
+    assert torch.equal(lse, lse2)                                   # LSE does not depend on V
+    out_2v, _ = ops.attn_fwd(q2, k2, (v2.float() * 2).bfloat16(), B, nh, L, L)
+    _close(out_2v, out.float() * 2, tol=1e-2, name="linearity in V")
+    # spot rows against fp32 SDPA
+    rows = torch.arange(0, L, L // 64, device=cuda_dev)[:64]
+    qf = rearrange(q2.reshape(B, L, nh, hd), "b l h d -> b h l d").float()[:, :, rows]
+    kf = rearrange(k2.reshape(B, L, nh, hd), "b l h d -> b h l d").float()
+    vf = rearrange(v2.reshape(B, L, nh, hd), "b l h d -> b h l d").float()
+    ref = F.scaled_dot_product_attention(qf, kf, vf)
+    got = rearrange(out.view(B, L, nh, hd), "b l h d -> b h l d")[:, :, rows]
+    _close(got, ref, tol=2e-2, name="spot rows")
+    # backward: linear in dO; dq of a constant-V problem is zero (softmax rows sum to one => dP - delta = 0)
+    d_o = _r((B * L, h), cuda_dev, 51)
+
+    def bwd(vv, oo, dd):
+        dq = torch.zeros((B * L, h), device=cuda_dev, dtype=torch.float32)
+        dk = torch.zeros((B * L, h), device=cuda_dev, dtype=torch.bfloat16)
+        dv = torch.zeros_like(dk)
+        ops.attn_bwd(q2, k2, vv, oo, dd, lse, B, nh, L, L, dq, dk=dk, dv=dv)
+        return dq, dk.float(), dv.float()
+    dq, dk, dv = bwd(v2, out, d_o)
+    dq2, dk2, dv2 = bwd(v2, out, (d_o.float() * 2).bfloat16())
+    for a, b_, name in ((dq2, dq * 2, "dq"), (dk2, dk * 2, "dk"), (dv2, dv * 2, "dv")):
+        assert _cos(a, b_) > 0.9999, (name, _cos(a, b_))
+        _close(a, b_, tol=2e-2, name=name + " linearity in dO")
+    dq_c, dk_c, dv_c = bwd(ones, out1, d_o)
+    scale = dq.abs().max().item()
+    assert dq_c.abs().max().item() < 2e-2 * scale and dk_c.abs().max().item() < 2e-2 * dk.abs().max().item()
+    # dV = P^T dO: summed over keys it equals the sum of dO over queries (columns of P^T sum ... rows of P sum to one)
+    tot_dv = rearrange(dv.view(B, L, nh, hd), "b l h d -> b h l d").sum(2)
+    tot_do = rearrange(d_o.float().view(B, L, nh, hd), "b l h d -> b h l d").sum(2)
+    _close(tot_dv, tot_do, tol=2e-2, name="sum_k dV == sum_q dO")
+
+
 def test_loss_fwd_bwd(cuda_dev):
     from vds_b200 import ops
     B, shape = 2, (2, 16, 4, 8, 8)
