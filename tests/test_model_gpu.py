@@ -106,6 +106,23 @@ def test_debug_width_vs_oracle(cuda_dev, train_bias):
     _compare("torch-bf16 eager vs fp32 oracle (context)", bl, bg, rl, rg, min_cos=0.98)
 
 
+def test_full_sequence_debug_vs_oracle(cuda_dev):
+    """bench.py's exact per-block shapes (S_dbg: B=2 x [16,16,64,64] latents -> L = 8208 tokens, h = 512, 4 heads,
+    context [2,512,4096]) at depth 2, against the fp32 oracle run on the GPU: this is the size at which the tail-balanced
+    attention backward, the 2-CTA GEMM tiles, the fused epilogues and the STORE_ROWDOT delta are actually selected."""
+    cfg = dict(in_channels=16, patch_size=2, time_patch_size=2, hidden_size=512, depth=2, num_heads=4,
+               mlp_ratio=4.0, cross_attn_input_size=4096, residual_v=True, train_bias_and_rms=False, use_rope=True)
+    model = build_model(cfg, 0, 1).to(cuda_dev)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 2 and not any(z in n for z in O.ZERO_INIT):
+                p.mul_(0.1)
+    latent, noise, context, t = [a.to(cuda_dev) for a in O.make_inputs(cfg, 2, (16, 64, 64), 512, 4096, 8)]
+    loss, _, grads = _cuda_step(model, latent, noise, context, t, 123, fused=True)
+    rl, _, rg = _oracle_step(model, cfg, latent, noise, context, t, 123, (8, 32, 32), torch.float32, cuda_dev)
+    _compare("S_dbg full sequence (L=8208), depth 2", loss, grads, rl, rg)
+
+
 def test_forward_only_and_eval(cuda_dev):
     fx, cfg, model, (latent, noise, context, t) = golden_case("tiny_nobias")
     model = model.to(cuda_dev, torch.bfloat16).eval()   # sample.py:63 style: bf16 module incl. bf16 rope tables
