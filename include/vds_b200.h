@@ -136,7 +136,9 @@ int vds_accum_bf16_f32(const void* x, float* y, int64_t n, int accumulate, void*
  * on tcgen05/TMEM with TMA producers.  q/k/v/out are token-major [B, L, ld] buffers with head i at column
  * i*128 (so "(k h d)" / "b h l d -> b l (h d)" rearranges, model.py:126,137, need no copies).
  * lse: [B, nh, Lq] fp32 in the log2 domain.  Backward: dq_acc is a zero-initialised fp32 buffer reduced
- * into with red.global.add; with q_splits > 1 dk/dv are reduced into fp32 dk_acc/dv_acc instead. */
+ * into with red.global.add; with q_splits > 1 dk/dv are reduced into fp32 dk_acc/dv_acc instead.
+ * delta [B, nh, Lq] fp32 = rowsum(dO * O) per head: computed here from o and d_o, or, with o == NULL, taken as
+ * given (the dgrad GEMM that produced d_o wrote it through VDS_EPI_STORE_ROWDOT). */
 int vds_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                  int64_t ldo, float* lse, int B, int nh, int Lq, int Lk, int head_dim, float scale, void* stream);
 int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
