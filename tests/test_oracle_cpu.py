@@ -149,3 +149,25 @@ def test_gelu_logistic_fit():
         assert abs(float(coef[f"W{k}"]) + (2 * k + 1) * float(coef[f"Q{k}"]) / 1.4426950408889634) < 1e-6 * (1 + abs(float(coef[f"W{k}"])))
     # saturating tails: exactly 0 / x
     assert g[0] == 0 and g[-1] == x[-1]
+
+
+def test_sampling_loop_pinned_to_reference_generate_image():
+    """tests/golden/sampling_tiny.pt was produced by the UNMODIFIED reference sampling/sample.py:generate_image (UI /
+    T5 / decoder modules stubbed, oracle/gen_golden_sampling.py): the oracle's restated loop must reproduce its final
+    latents — same shifted-time Euler steps, CFG, fp32 accumulator and RNG consumption (2 x 3 RoPE draws per step)."""
+    import vds_b200  # noqa: F401
+    from vds_b200.model import DiT
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "sampling_tiny.pt"), weights_only=False)
+    torch.manual_seed(fx["seed_model"])
+    m = DiT(**fx["cfg"])                       # same constructor RNG consumption as the reference's DiT
+    sd = O.randomise_zero_init({k: v.clone() for k, v in m.state_dict().items() if "freqs_hwt" not in k},
+                               seed=fx["seed_zero"])
+    for k, n in fx["param_norms"].items():
+        assert abs(sd[k].float().norm().item() - n) <= 1e-6 * (1 + n), k
+    torch.manual_seed(fx["seed_rng"])
+    got = O.sample_loop(sd, fx["cfg"], fx["prompt_embeds"], fx["lat0"], fx["steps"], cfg_scale=fx["cfg_scale"],
+                        table_dtype=torch.float32, model_dtype=torch.float32)
+    assert got.dtype == torch.float32
+    err = (got.squeeze(0) - fx["final"]).abs().max().item()
+    assert err <= 1e-5 * fx["final"].abs().max().item(), err
+    assert fx["oracle_max_abs_err_at_generation"] == 0.0
