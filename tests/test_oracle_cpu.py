@@ -171,3 +171,35 @@ def test_sampling_loop_pinned_to_reference_generate_image():
     err = (got.squeeze(0) - fx["final"]).abs().max().item()
     assert err <= 1e-5 * fx["final"].abs().max().item(), err
     assert fx["oracle_max_abs_err_at_generation"] == 0.0
+
+
+def test_train_glue_pinned_to_reference_train_forward():
+    """tests/golden/trainglue_tiny.pt holds the loss of the UNMODIFIED reference train.py:forward (utils stubbed,
+    oracle/gen_golden_trainglue.py) on a tiny bf16 DiT on the CPU.  The oracle's restated glue — bf16 cast, caption
+    zero-out draw, t = shift(sigmoid(N(0,1))), noise, z_t, v-target, per-sample MSE, batch mean (train.py:73-125) —
+    must reproduce it, consuming both RNG streams (the passed generator and the global one) in the same order."""
+    import vds_b200  # noqa: F401
+    from vds_b200.model import DiT
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "trainglue_tiny.pt"), weights_only=False)
+    cfg = fx["cfg"]
+    torch.manual_seed(fx["seed_model"])
+    m = DiT(**cfg)
+    sd = O.randomise_zero_init({k: v.clone() for k, v in m.state_dict().items() if "freqs_hwt" not in k},
+                               seed=fx["seed_zero"])
+    for k, n in fx["param_norms"].items():
+        assert abs(sd[k].float().norm().item() - n) <= 1e-6 * (1 + n), k
+    latent, caption = fx["latent"], fx["caption"]
+    B = latent.shape[0]
+    gen = torch.Generator().manual_seed(fx["seed_gen"])
+    torch.manual_seed(fx["seed_global"])
+    lat16, cap16 = latent.to(torch.bfloat16), caption.to(torch.bfloat16)
+    zero = torch.rand(B) < 0.01
+    cap16[zero] = 0
+    t = O.sample_timesteps(B, "cpu", torch.bfloat16, gen)
+    assert torch.equal(t, fx["t"])
+    noise = torch.randn(lat16.shape, dtype=torch.bfloat16, generator=gen)
+    starts = O.draw_rope_starts(tuple(d // 2 for d in latent.shape[2:]))
+    P16 = {k: v.to(torch.bfloat16) for k, v in sd.items()}
+    loss, _ = O.train_loss(P16, cfg, lat16, cap16, t, noise, rope_starts=starts, table_dtype=torch.bfloat16)
+    assert abs(loss.item() - fx["loss"]) <= 1e-6 * abs(fx["loss"]), (loss.item(), fx["loss"])
+    assert fx["oracle_abs_err_at_generation"] == 0.0
