@@ -425,7 +425,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* gSTG = reinterpret_cast<float*>(gen + BWD_OFF_STG);
   float* s_stat = reinterpret_cast<float*>(gen + BWD_OFF_STAT);   // [buf][lse|delta][64]
   const uint32_t bars = base + BWD_OFF_BAR;
-  const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 32, sdp_full = bars + 56,
+  const uint32_t kv_full = bars, qdo_full = bars + 8, qdo_empty = bars + 32, s_full = bars + 56,
                  pds_full = bars + 72, mma_done = bars + 80, dq_drained = bars + 96, tmem_slot = bars + 112,
                  stat_full = bars + 120, dp_full = bars + 136, dp_read = bars + 144, dq_full = bars + 152;
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + BWD_OFF_BAR + 112);
@@ -445,7 +445,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(kv_full, 1);
     for (int s = 0; s < 3; ++s) { mbar_init(qdo_full + 8 * s, 1); mbar_init(qdo_empty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(sdp_full + 8 * s, 1);
+      mbar_init(s_full + 8 * s, 1);
       mbar_init(mma_done + 8 * s, 1);
       mbar_init(dq_drained + 8 * s, 128);
       mbar_init(stat_full + 8 * s, 128);
@@ -511,7 +511,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_bf16(tST, desc_kmajor(sK, kk), umma_smem_desc(q + (kk >> 2) * QT_HALF + (kk & 3) * 32, 16, 1024),
                       idesc_s, kk > 0);
           umma_bf16(tST, desc_k16_noswz(sPT), desc_k16_noswz(sPT + 4096 + (bb * 2 + 0) * 2048), idesc_s, 1);  // - lse
-          umma_commit(sdp_full + 8 * bb);
+          umma_commit(s_full + 8 * bb);
           VDS_TRACE(7, k);   // S(k) issued
         }
         __syncwarp();
@@ -612,7 +612,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int i = 0; i < n_q; ++i) {
         const int bb = i & 1;
         const float next_raw = (i + 2 < n_q) ? stat_fetch(i + 2) : 0.f;   // prefetched; stored at the end of this iteration
-        mbar_wait(sdp_full + 8 * bb, (i >> 1) & 1);
+        mbar_wait(s_full + 8 * bb, (i >> 1) & 1);
         tc_fence_after();
         if (ct == 0) VDS_TRACE(2, i);   // compute sees S(i)
         const uint32_t tST = tSTb + bb * 64 + lane_off, tDPT = tDPTs + lane_off;
