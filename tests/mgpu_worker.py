@@ -18,12 +18,24 @@ from vds_b200.model import apply_fsdp  # noqa: E402
 from vds_b200.optim import FusedAdamW  # noqa: E402
 
 CONST = ["patch_proj", "context_kv", "positional_embedding"]
-CFG = dict(in_channels=16, patch_size=2, time_patch_size=2, hidden_size=256, depth=3, num_heads=2, mlp_ratio=4.0,
-           cross_attn_input_size=64, residual_v=True, train_bias_and_rms=True, use_rope=True)
+# VDS_MGPU_CFG=debug: the run_debug.sh width (512, 4 heads x 128, T5-width context) at depth 3 on a [4,16,16] latent;
+# default: the tiny 256-wide model.  VDS_MGPU_GRAPH=1: the sharded steps go through train.GraphedTrainStep (NCCL
+# all-gathers / reduce-scatters captured inside the CUDA graph) instead of the Python-issued step.
+DEBUG_W = os.environ.get("VDS_MGPU_CFG", "tiny") == "debug"
+GRAPH = os.environ.get("VDS_MGPU_GRAPH", "0") == "1"
+NSTEPS = 4 if GRAPH else 2
+if DEBUG_W:
+    CFG = dict(in_channels=16, patch_size=2, time_patch_size=2, hidden_size=512, depth=3, num_heads=4, mlp_ratio=4.0,
+               cross_attn_input_size=4096, residual_v=True, train_bias_and_rms=False, use_rope=True)
+    DATA = (2, (4, 16, 16), 512, 4096)
+else:
+    CFG = dict(in_channels=16, patch_size=2, time_patch_size=2, hidden_size=256, depth=3, num_heads=2, mlp_ratio=4.0,
+               cross_attn_input_size=64, residual_v=True, train_bias_and_rms=True, use_rope=True)
+    DATA = (2, (4, 8, 8), 24, 64)
 
 
 def data(rank, dev):
-    return [a.to(dev) for a in O.make_inputs(CFG, 2, (4, 8, 8), 24, 64, 100 + rank)]
+    return [a.to(dev) for a in O.make_inputs(CFG, DATA[0], DATA[1], DATA[2], DATA[3], 100 + rank)]
 
 
 def main():
@@ -36,16 +48,22 @@ def main():
     opt = FusedAdamW(groups, betas=(0.95, 0.99), flat=model._flat)
     latent, noise, context, t = data(rank, dev)
     losses = []
-    for step in range(2):
-        opt.zero_grad()
+    stepper = train.GraphedTrainStep(model, opt, latent.shape, context.shape, device=dev, warmup=1) if GRAPH else None
+    for step in range(NSTEPS):
         torch.manual_seed(50 + step)
-        loss, _ = train.forward(model, latent, context, t=t, noise=noise)
-        loss.backward()
-        opt.step()
+        if stepper is not None:     # step 0 eager on the capture stream, step 1 captures + replays, steps 2.. replay
+            loss = stepper(latent, context, t, noise, caption_dropout=0.0).clone()
+        else:
+            opt.zero_grad()
+            loss, _ = train.forward(model, latent, context, t=t, noise=noise, caption_dropout=0.0)
+            loss.backward()
+            opt.step()
         losses.append(loss.detach())
     torch.cuda.synchronize()
+    if stepper is not None:
+        assert stepper.graph is not None, "the multi-GPU step was not captured"
     sd = model.state_dict()  # full tensors (all-gathers the fp32 master shards)
-    all_loss = [torch.zeros(2, device=dev) for _ in range(world)]
+    all_loss = [torch.zeros(NSTEPS, device=dev) for _ in range(world)]
     dist.all_gather(all_loss, torch.stack(losses))
     dist.barrier()
     ok = True
@@ -54,13 +72,13 @@ def main():
         ref = build_model(CFG, 0, 1).to(dev)
         names = [n for n, _ in ref.named_parameters()]
         state = {n: (p.detach().clone(), torch.zeros_like(p), torch.zeros_like(p)) for n, p in ref.named_parameters()}
-        for step in range(2):
+        for step in range(NSTEPS):
             gsum = {}
             for r in range(world):
                 la, no, cx, tt = data(r, dev)
                 ref.zero_grad(set_to_none=True)
                 torch.manual_seed(50 + step)
-                loss, _ = train.forward(ref, la, cx, t=tt, noise=no)
+                loss, _ = train.forward(ref, la, cx, t=tt, noise=no, caption_dropout=0.0)
                 loss.backward()
                 if abs(loss.item() - all_loss[r][step].item()) > 2e-3 * abs(loss.item()):
                     print(f"loss mismatch step {step} rank {r}: {loss.item()} vs {all_loss[r][step].item()}")
@@ -83,8 +101,8 @@ def main():
             if c < 0.9999 or rel > 2e-2:
                 print(f"param mismatch {n}: cos {c:.6f} rel {rel:.3e}")
                 ok = False
-        print(f"MGPU world={world}: worst param cosine after 2 sharded steps vs single-GPU reference {worst:.6f}; "
-              f"{'OK' if ok else 'FAIL'}")
+        print(f"MGPU world={world} cfg={'debug' if DEBUG_W else 'tiny'} graph={int(GRAPH)}: worst param cosine after "
+              f"{NSTEPS} sharded steps vs single-GPU reference {worst:.6f}; {'OK' if ok else 'FAIL'}")
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -30,7 +30,7 @@ def test_flat_step_and_fused_adamw(cuda_dev):
     for step in (1, 2):
         opt.zero_grad()
         torch.manual_seed(fx["seeds"]["rope"])
-        loss, _ = train.forward(model, latent, context, t=t, noise=noise)
+        loss, _ = train.forward(model, latent, context, t=t, noise=noise, caption_dropout=0.0)
         loss.backward()
         grads = {n: (p.grad.detach().clone() if p.grad is not None else None) for n, p in model.named_parameters()}
         if step == 1:
@@ -69,7 +69,7 @@ def test_stock_torch_adamw_on_flat_params(cuda_dev):
     for step in range(3):
         opt.zero_grad()
         torch.manual_seed(fx["seeds"]["rope"])
-        loss, _ = train.forward(model, latent, context, t=t, noise=noise)
+        loss, _ = train.forward(model, latent, context, t=t, noise=noise, caption_dropout=0.0)
         loss.backward()
         opt.step()
         losses.append(loss.item())
@@ -95,10 +95,10 @@ def test_graphed_train_step_matches_eager(cuda_dev):
             for g in opt.param_groups:          # a moving learning rate, as a scheduler would produce
                 g["lr"] = g["lr"] * 0.9
             if graphed:
-                loss = stepper(latent, context, t, noise)
+                loss = stepper(latent, context, t, noise, caption_dropout=0.0)
             else:
                 opt.zero_grad()
-                loss, _ = train.forward(model, latent, context, t=t, noise=noise)
+                loss, _ = train.forward(model, latent, context, t=t, noise=noise, caption_dropout=0.0)
                 loss.backward()
                 opt.step()
             losses.append(loss.item())

@@ -18,7 +18,7 @@ def _cuda_step(model, latent, noise, context, t, seed, fused):
     model.zero_grad(set_to_none=True)
     torch.manual_seed(seed)
     if fused:
-        loss, _ = train.forward(model, latent, context, t=t, noise=noise)
+        loss, _ = train.forward(model, latent, context, t=t, noise=noise, caption_dropout=0.0)
         out = None
     else:
         tr = t.reshape(-1, 1, 1, 1, 1)
@@ -190,3 +190,32 @@ def test_ragged_and_tiny_shapes_vs_oracle(cuda_dev, B, latent_thw, Lc):
     thw = tuple(d // 2 for d in latent_thw)
     rl, _, rg = _oracle_step(model, cfg, latent, noise, context, t, 13, thw, torch.float32, cuda_dev)
     _compare(f"B={B} thw={latent_thw}", loss, grads, rl, rg)
+
+
+def test_caption_dropout_is_applied_by_the_product_path(cuda_dev):
+    """train.py:86-87: the product train.forward (and the graphed step) zeroes a sample's caption embedding with
+    probability p, drawn from the global generator of the caption's device.  p = 1 must give exactly the loss of an
+    all-zero context, p = 0 must leave the context alone, and a seeded p = 0.5 draw must zero exactly the samples the
+    same ``torch.rand(B, device) < p`` draw selects."""
+    from vds_b200 import train
+    fx, cfg, model, (latent, noise, context, t) = golden_case("tiny_nobias")
+    model = model.to(cuda_dev)
+    latent, noise, context, t = [a.to(cuda_dev) for a in (latent, noise, context, t)]
+
+    def loss_of(ctx, p):
+        torch.manual_seed(11)
+        with torch.no_grad():
+            return train.forward(model, latent, ctx, t=t, noise=noise, caption_dropout=p)[0].item()
+
+    keep, zero = loss_of(context, 0.0), loss_of(torch.zeros_like(context), 0.0)
+    assert keep != zero
+    assert loss_of(context, 1.0) == zero
+    torch.cuda.manual_seed(5)
+    torch.manual_seed(5)
+    expect = torch.rand(context.shape[0], device=cuda_dev) < 0.5
+    torch.cuda.manual_seed(5)
+    torch.manual_seed(5)
+    got = train.drop_captions(context.to(torch.bfloat16), 0.5)
+    assert torch.equal(got.float().abs().sum(dim=(1, 2)) == 0, expect)
+    assert torch.equal(got[~expect], context.to(torch.bfloat16)[~expect])
+    assert context.abs().sum().item() > 0          # the caller's tensor is left alone

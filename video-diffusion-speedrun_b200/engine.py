@@ -85,6 +85,7 @@ def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise
     t_bf = timesteps.to(device=dev, dtype=torch.bfloat16).contiguous()
     if has_cross:
         ctx2d = context.to(torch.bfloat16).contiguous().view(-1, context.shape[-1])
+        ctx_is_callers = ctx2d.data_ptr() == context.data_ptr()   # no temporary copy was made
         Lc = context.shape[1]
 
     c = Ctx()
@@ -141,14 +142,19 @@ def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise
                                             weight=P.get(pre + "norm2.weight"), want_rstd=save)
             qc = ops.gemm(n2, P[pre + "q_cross.weight"], bias=P.get(pre + "q_cross.bias"))
             ckv = None
-            cache = getattr(model, "_ckv_cache", None) if not save else None
-            if cache is not None:   # inference: context_kv(context) depends only on the prompt, not on the step (§8f n2)
-                key = (i, ctx2d.data_ptr(), ctx2d._version, tuple(ctx2d.shape))
-                ckv = cache.get(key)
+            # inference: context_kv(context) depends only on the prompt, not on the step (§8f n2).  The entry keeps the
+            # context tensor itself alive and a hit needs the SAME tensor object at the same version: a freed temporary
+            # whose address the allocator hands to the next prompt can never alias an entry.  When the engine had to
+            # make its own bf16 / contiguous copy of `context` the copy dies with this call, so the cache is bypassed.
+            cache = getattr(model, "_ckv_cache", None) if (not save and ctx_is_callers) else None
+            if cache is not None:
+                ent = cache.get((i, id(context)))   # the entry holds `context`, so its id cannot be recycled
+                if ent is not None and ent[0] is context and ent[1] == context._version:
+                    ckv = ent[2]
             if ckv is None:
                 ckv = ops.gemm(ctx2d, P[pre + "context_kv.weight"], bias=P.get(pre + "context_kv.bias"))
                 if cache is not None:
-                    cache[key] = ckv
+                    cache[(i, id(context))] = (context, context._version, ckv)
             ca, lse2 = ops.attn_fwd(qc, ckv[:, :h], ckv[:, h:], B, nh, Lr, Lc, want_lse=save)
             o2, X2 = ops.gemm(ca, P[pre + "cross_proj.weight"], epilogue=L.EPI_GATE_RES, aux=X1, gate=gate_ca,
                               rows_per_batch=Lr)
@@ -234,6 +240,27 @@ def _attn_q_splits(n_kv_tiles, B, nh, n_q_tiles, sms=148):
     return best
 
 
+class ZeroArena:
+    """The zero-initialised fp32 accumulation targets of ONE block's backward (dmod, the two delta vectors, the two
+    fp32 dq buffers, the split-query dk/dv buffer) carved out of one allocation, so a block costs one fill launch
+    instead of six ``torch.zeros`` (0.7 ms / step of FillFunctor launches at debug-8k).  The arena is reused by every
+    block of a backward pass: all work is stream-ordered, block i's readers are enqueued before block i-1's fill."""
+
+    def __init__(self, dev, sizes):
+        self.off, n = {}, 0
+        for name, numel in sizes.items():
+            self.off[name] = (n, numel)
+            n += (numel + 63) // 64 * 64          # 256-byte aligned slices (TMA reduce target needs 16)
+        self.buf = torch.empty(max(n, 64), device=dev, dtype=torch.float32)
+
+    def reset(self):
+        self.buf.zero_()
+
+    def get(self, name, shape):
+        o, numel = self.off[name]
+        return self.buf[o:o + numel].view(shape)
+
+
 def backward(model, P, c, dout, sink):
     """Accumulates every parameter gradient into `sink`; returns nothing (x / context / t get no grad)."""
     B, C, T, H, W = c.shape
@@ -262,11 +289,20 @@ def backward(model, P, c, dout, sink):
     ops.gemm(dfmod_b, P["final_modulation.1.weight"], b_mn=True, epilogue=L.EPI_ACCUM_F32, out=dsc_acc)
 
     dv0_acc = torch.zeros((B * Lr, h), **f32) if (c.residual_v and depth > 1) else None
+    sizes = {"dmod": B * 9 * h, "delta1": B * nh * Lr, "dq_self": B * Lr * h}
+    qs = 1
+    if c.has_cross:
+        qs = _attn_q_splits((c.Lc + 127) // 128, B, nh, (Lr + 127) // 128)
+        sizes.update({"delta2": B * nh * Lr, "dq_cross": B * Lr * h})
+        if qs > 1:
+            sizes["dckv_f"] = B * c.Lc * 2 * h
+    arena = ZeroArena(dev, sizes)
     for i in reversed(range(depth)):
         pre = f"blocks.{i}."
         s = c.blocks[i]
         shift_sa, scale_sa, gate_sa, shift_ca, scale_ca, gate_ca, shift_mlp, scale_mlp, gate_mlp = _chunks(s.mod, h)
-        dmod = torch.zeros((B, 9 * h), **f32)
+        arena.reset()
+        dmod = arena.get("dmod", (B, 9 * h))
         dm = _chunks(dmod, h)
         # ---- MLP branch
         do3 = ops.gate_bwd(dX, s.o3, gate_mlp, dm[8], B, Lr, h)
@@ -284,14 +320,13 @@ def backward(model, P, c, dout, sink):
             Lc = c.Lc
             do2 = ops.gate_bwd(dX2, s.o2, gate_ca, dm[5], B, Lr, h)
             sink.wgrad(pre + "cross_proj.weight", do2, s.ca)
-            delta2 = torch.zeros((B, nh, Lr), **f32)
+            delta2 = arena.get("delta2", (B, nh, Lr))
             dca = ops.gemm_dgrad_rowdot(do2, P[pre + "cross_proj.weight"], s.ca, delta2, Lr)
             if dca is None:
                 dca, delta2 = ops.gemm(do2, P[pre + "cross_proj.weight"], b_mn=True), None
-            dq_acc = torch.zeros((B * Lr, h), **f32)
-            qs = _attn_q_splits((Lc + 127) // 128, B, nh, (Lr + 127) // 128)
+            dq_acc = arena.get("dq_cross", (B * Lr, h))
             if qs > 1:
-                dckv_f = torch.zeros((B * Lc, 2 * h), **f32)
+                dckv_f = arena.get("dckv_f", (B * Lc, 2 * h))
                 ops.attn_bwd(s.qc, s.ckv[:, :h], s.ckv[:, h:], s.ca, dca, s.lse2, B, nh, Lr, Lc, dq_acc,
                              dk_acc=dckv_f[:, :h], dv_acc=dckv_f[:, h:], q_splits=qs, delta=delta2)
                 dckv = ops.cast_f32_bf16(dckv_f)
@@ -314,12 +349,12 @@ def backward(model, P, c, dout, sink):
         # ---- self-attention branch
         do1 = ops.gate_bwd(dX1, s.o1, gate_sa, dm[2], B, Lr, h)
         sink.wgrad(pre + "attn_proj.weight", do1, s.a)
-        delta1 = torch.zeros((B, nh, Lr), **f32)
+        delta1 = arena.get("delta1", (B, nh, Lr))
         da = ops.gemm_dgrad_rowdot(do1, P[pre + "attn_proj.weight"], s.a, delta1, Lr)   # dO and delta = rowsum(dO * O)
         if da is None:
             da, delta1 = ops.gemm(do1, P[pre + "attn_proj.weight"], b_mn=True), None
         dqkv = torch.empty((B * Lr, 3 * h), device=dev, dtype=torch.bfloat16)
-        dq_acc = torch.zeros((B * Lr, h), **f32)
+        dq_acc = arena.get("dq_self", (B * Lr, h))
         ops.attn_bwd(s.qkv[:, :h], s.qkv[:, h:2 * h], s.V, s.a, da, s.lse, B, nh, Lr, Lr, dq_acc, dk=dqkv[:, h:2 * h],
                      dv=dqkv[:, 2 * h:], delta=delta1)
         if s.use_mix:

@@ -37,7 +37,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self.hyper_dev = None   # set by train.GraphedTrainStep: device copy of [lr | wd | bc1 | sqrt(bc2)]
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, gather=True):
+        """One fused AdamW update of this rank's shard.  `gather=False` skips the parameter all-gather that normally
+        follows (train.GraphedTrainStep at world size > 1 issues it at the top of the next captured step instead)."""
         assert closure is None
         flat = self.flat
         self._step += 1
@@ -52,7 +54,10 @@ class FusedAdamW(torch.optim.Optimizer):
                                   b1, b2, eps, self._step, 1.0,
                                   self.hyper_dev.data_ptr() if self.hyper_dev is not None else None,
                                   torch.cuda.current_stream().cuda_stream), "vds_adamw")
-        flat.gather_params()  # side stream; the next forward waits per group
+        if gather:
+            flat.gather_params()  # side stream; the next forward waits per group
+        else:
+            flat._gather_pending = flat.world > 1
         return None
 
     def hyper_values(self, step):

@@ -137,6 +137,7 @@ class FlatShards:
         self.ag_events = [None] * (self.depth + 1)
         self.rs_events = []
         self._fresh = False
+        self._gather_pending = False
         self.refresh_from_master()
 
     @staticmethod
@@ -189,6 +190,7 @@ class FlatShards:
 
     def gather_params(self):
         """All-gather every group's bf16 shard on the side stream (root group first, then block 0, 1, ...)."""
+        self._gather_pending = False
         order = [self.depth] + list(range(self.depth))
         if self.world == 1:
             return  # shard16 aliases full16
@@ -214,6 +216,10 @@ class FlatShards:
     def compute_params(self):
         if self.master._version != self._seen_version:
             self.refresh_from_master()
+        elif self._gather_pending:
+            # the last optimizer step left the gather to "the next step" (FusedAdamW.step(gather=False), used by the
+            # graphed multi-GPU step): an eager forward that follows must not read the stale gathered copy
+            self.gather_params()
         return self._pview
 
     def wait_group(self, g):
@@ -225,8 +231,10 @@ class FlatShards:
 
     # ------------------------------------------------------------------------------ gradients
     def begin_backward(self):
-        first = next(iter(self.params.values()))
-        self._accumulate = first.grad is not None
+        # "accumulate" = some trainable parameter still carries the .grad view a previous backward handed out (i.e. no
+        # zero_grad in between).  Frozen parameters never get a .grad here (end_backward), so one frozen / optimizer-less
+        # tensor cannot pin the buffer in accumulate mode.
+        self._accumulate = any(p.grad is not None for p in self.params.values() if p.requires_grad)
         if self._accumulate and self.world > 1:
             raise NotImplementedError("gradient accumulation over several backward passes needs world_size 1")
         if not self._accumulate:
@@ -262,6 +270,8 @@ class FlatShards:
         for n, p in self.params.items():
             if n.endswith("blocks.0.lambda_param"):
                 continue  # never used by block 0 (model.py:129): the reference leaves .grad = None too
+            if not p.requires_grad:
+                continue  # frozen: autograd would leave .grad = None as well
             if p.grad is None:
                 s, _, ln = lay.shard_range(n, self.rank)
                 p.grad = self.gshard[s:s + ln].view(p.shape)

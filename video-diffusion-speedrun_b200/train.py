@@ -41,12 +41,32 @@ class TrainStepFunction(torch.autograd.Function):
         return (None, None, None, None, None, None, None) + grads
 
 
-def forward(dit_model, latent, caption_encoded, generator=None, t=None, noise=None, rope_starts_dev=None):
+CAPTION_DROPOUT = 0.01   # train.py:86
+
+
+def drop_captions(caption_encoded, p=CAPTION_DROPOUT, out=None):
+    """train.py:86-87: with probability 1 % the whole caption embedding of a sample is zeroed (this zero embedding is
+    what sampling/sample.py:104 uses as the CFG negative).  The draw is ``torch.rand(B, device=device)`` on the global
+    generator of the caption's device, like the reference.  Written as a mask fill (no ``nonzero`` host sync, so it can
+    sit in front of a CUDA-graph replay); `out` = fill in place."""
+    if p <= 0.0:
+        return caption_encoded
+    do_zero_out = torch.rand(caption_encoded.shape[0], device=caption_encoded.device) < p
+    mask = do_zero_out.view(-1, *([1] * (caption_encoded.dim() - 1)))
+    if out is not None:
+        return out.masked_fill_(mask, 0)
+    return caption_encoded.masked_fill(mask, 0)
+
+
+def forward(dit_model, latent, caption_encoded, generator=None, t=None, noise=None, rope_starts_dev=None,
+            caption_dropout=CAPTION_DROPOUT):
     """train.py:51-145 on the fused path.  latent [B,16,T,H,W], caption_encoded [B,512,4096] (bf16, CUDA).
-    `t` / `noise` may be supplied (parity tests); otherwise drawn exactly like train.py:89-105."""
+    `t` / `noise` may be supplied (parity tests); otherwise drawn exactly like train.py:89-105.  The 1 % caption
+    zero-out of train.py:86-87 is applied here (`caption_dropout=0` turns it off for parity tests)."""
     device = latent.device
     vae_latent = latent.to(torch.bfloat16).contiguous()  # train.py:73
     batch_size = vae_latent.size(0)
+    caption_encoded = drop_captions(caption_encoded.to(torch.bfloat16), caption_dropout)  # train.py:84-87
     if t is None:
         z = torch.randn(batch_size, device=device, dtype=torch.bfloat16, generator=generator)
         t = shift_time(torch.sigmoid(z))
@@ -66,14 +86,20 @@ class GraphedTrainStep:
 
     Everything that changes from step to step lives in device buffers that are refreshed before each replay: the
     batch, the RoPE start offsets (still drawn from the global CPU generator in the reference's order h, w, t) and the
-    optimizer scalars (per-group lr / wd, bias corrections).  World size 1 only (the per-block NCCL collectives of the
-    sharded path are issued from Python).  ~1100 kernel launches become one graph launch, which is what the small
-    workloads (DiT-B at 256x256, the S_small debug shape) are bound by.
+    optimizer scalars (per-group lr / wd, bias corrections).  ~1100 kernel launches become one graph launch, which is
+    what the small workloads (DiT-B at 256x256, the S_small debug shape) are bound by.
+
+    World size > 1: the graph also holds the collectives of shard.FlatShards on their side stream — the bf16 parameter
+    all-gathers are issued at the TOP of the captured step (root group, block 0, 1, ...; the forward waits per group,
+    so they overlap the forward exactly like the eager path's post-optimizer gathers overlap the next forward) and the
+    per-block fp32 reduce-scatters are forked off the backward.  Every fork joins the capture stream again inside the
+    step (the forward waits for every group, end_backward for every reduce-scatter), which is what stream capture
+    requires.  The host issues ONE graph launch per step on every rank.
     """
 
     def __init__(self, model, optimizer, latent_shape, context_shape, device="cuda", warmup=2):
         from . import engine as _engine
-        assert model._flat is not None and model._flat.world == 1, "GraphedTrainStep: apply_fsdp(model) at world size 1"
+        assert model._flat is not None, "GraphedTrainStep needs apply_fsdp(model) (flat parameter / gradient buffers)"
         self.model, self.opt, self._engine = model, optimizer, _engine
         dev = torch.device(device)
         bf = dict(device=dev, dtype=torch.bfloat16)
@@ -104,24 +130,36 @@ class GraphedTrainStep:
         """The step without torch.autograd in the loop (the engine's forward / backward are called directly), so the
         capture contains only our kernels + memsets and no autograd-engine stream bookkeeping."""
         model, eng = self.model, self._engine
+        sharded = model._flat.world > 1
         with torch.no_grad():
             self.opt.zero_grad()
+            if sharded:
+                model._flat.gather_params()      # side stream; consumed group by group by the forward below
             P = model._param_view()
             out, c = eng.forward(model, P, self.latent, self.context, self.t, save=True, noise=self.noise,
                                  rope_starts_dev=self.starts_dev)
             loss, d_out, lb = ops.loss_fwd_bwd(self.latent, self.noise, out, want_grad=True, want_batch=True)
             model.last_loss_batchwise = lb
             eng.run_backward(model, P, c, d_out, None)
-            self.opt.step()
+            self.opt.step(gather=not sharded)    # sharded: the next step's graph gathers at its top
         return loss.view(())
 
-    def __call__(self, latent, context, t, noise):
+    def __call__(self, latent, context, t, noise, caption_dropout=CAPTION_DROPOUT):
         self.latent.copy_(latent, non_blocking=True)
         self.context.copy_(context, non_blocking=True)
+        drop_captions(self.context, caption_dropout, out=self.context)   # train.py:86-87, outside the graph
         self.t.copy_(t, non_blocking=True)
         self.noise.copy_(noise, non_blocking=True)
         self._refresh_scalars()
+        # The device copy of the optimizer scalars is installed only while this call captures / replays: a later eager
+        # opt.step() (e.g. after falling back from the graph) must read lr / wd / bias corrections by value again.
         self.opt.hyper_dev = self.hyper_dev
+        try:
+            return self._run()
+        finally:
+            self.opt.hyper_dev = None
+
+    def _run(self):
         if self.graph is None:
             # PyTorch's whole-network capture recipe: warm up on the side stream the capture will use (autograd's
             # stream bookkeeping must not reference work on the caller's stream), then capture there.
@@ -139,10 +177,13 @@ class GraphedTrainStep:
             self.graph = torch.cuda.CUDAGraph()
             step_before = self.opt._step
             n0 = _lib.launch_count()
-            with torch.cuda.graph(self.graph, stream=self._side):
+            # thread_local: NCCL's watchdog thread may touch the CUDA runtime while this thread captures
+            with torch.cuda.graph(self.graph, stream=self._side, capture_error_mode="thread_local"):
                 self.loss = self._step_body().detach()
             self.launches_per_step = _lib.launch_count() - n0   # kernels of ours inside one replay
             self.opt._step = step_before              # capture does not execute; the replay below is the real step
         self.graph.replay()
         self.opt._step += 1
+        flat = self.model._flat
+        flat._gather_pending = flat.world > 1    # the replayed step ended with an un-gathered optimizer update
         return self.loss
