@@ -152,6 +152,10 @@ int64_t vds_attn_bwd_tail_ws_bytes(int B, int nh, int Lk);
 
 /* tuning aid: per-iteration clock64 trace of one CTA of attn_bwd (NULL disables). */
 int vds_debug_attn_bwd_trace(void* buf);
+/* tests / tuning: which backward kernel serves self-attention-sized problems (q_splits == 1, bf16 dk / dv).
+ * -1: VDS_ATTN_PAIR environment variable (default auto); 0: the 1-CTA kernel only; 1: auto — whole waves of kv-tile
+ * pairs on the 2-CTA cluster kernel (tcgen05 cta_group::2), the rest on the 1-CTA kernel; 2: every pair on the cluster kernel. */
+int vds_debug_attn_pair_mode(int mode);
 /* tuning aid: CTA 0 of the 2-CTA GEMM writes {total, wait(tmem empty), wait(smem full), tiles, epi wait, epi busy} cycles. */
 int vds_debug_gemm2_trace(void* buf);
 

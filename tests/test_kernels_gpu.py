@@ -239,10 +239,25 @@ def _ref_attn(q, k, v):
     return F.scaled_dot_product_attention(q.float(), k.float(), v.float())
 
 
+@pytest.fixture
+def pair_mode():
+    """Selects the attention-backward kernel (vds_debug_attn_pair_mode) for one test and restores the default."""
+    from vds_b200 import lib as L
+
+    def set_mode(m):
+        L.check(L.lib().vds_debug_attn_pair_mode(m), "vds_debug_attn_pair_mode")
+    yield set_mode
+    set_mode(-1)
+
+
+@pytest.mark.parametrize("pair", [0, 2])    # 0: 1-CTA kernel only; 2: every kv-tile pair on the 2-CTA cluster kernel
 @pytest.mark.parametrize("B,nh,Lq,Lk", [(1, 1, 128, 128), (2, 4, 272, 272), (1, 2, 528, 512), (2, 4, 2064, 2064),
-                                        (3, 4, 2192, 2192)])   # 216 items on 148 SMs -> tail balancing path
-def test_attn_fwd_bwd(cuda_dev, B, nh, Lq, Lk):
+                                        (3, 4, 2192, 2192),    # 216 items on 148 SMs -> tail balancing path
+                                        (1, 2, 1040, 1040),    # 9 kv tiles: 4 pairs + an unpaired ragged tile per head
+                                        (1, 3, 200, 256)])     # one pair per head, ragged query range
+def test_attn_fwd_bwd(cuda_dev, pair_mode, pair, B, nh, Lq, Lk):
     from vds_b200 import ops
+    pair_mode(pair)
     hd, h = 128, nh * 128
     self_attn = Lq == Lk
     if self_attn:

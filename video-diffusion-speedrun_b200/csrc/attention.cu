@@ -14,35 +14,14 @@
 //   S^T = K Q^T, dP^T = V dO^T (TMEM) -> P^T, dS^T (smem, bf16) -> dV += P^T dO, dK += dS^T Q (TMEM),
 //   dQ tile = dS K (TMEM) reduced into an fp32 buffer with red.global.add.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.h"
 #include "ptx.cuh"
+#include "attn_common.cuh"
 
 namespace vds {
-
-constexpr int HD = 128;
-constexpr int ATT_THREADS = 192;
-constexpr int TILE_BYTES = 128 * HD * 2;  // 32 KiB: one 128 x 128 bf16 tile = two 64-wide SW128 halves
-constexpr int HALF_BYTES = TILE_BYTES / 2;
-
-// K-major operand tile (rows x 128 along the contraction): descriptor of 16-wide k-step kk
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kk) {
-  return umma_smem_desc(tile + (kk >> 2) * HALF_BYTES + (kk & 3) * 32, 16, 1024);
-}
-// MN-major operand tile (contraction index = smem row): 16 rows per k-step
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kk) {
-  return umma_smem_desc(tile + kk * 2048, HALF_BYTES, 1024);
-}
-
-__device__ __forceinline__ void load_tile_4d(uint32_t dst, const void* tmap, uint32_t bar, int row0, int head, int b) {
-  tma_load_4d(dst, tmap, bar, 0, row0, head, b);
-  tma_load_4d(dst + HALF_BYTES, tmap, bar, 64, row0, head, b);
-}
-
-// write 8 consecutive bf16 (columns c0..c0+7, c0 % 8 == 0) of row r into a K-major SW128 tile
-__device__ __forceinline__ void st_tile8(uint8_t* tile, int r, int c0, uint4 v) {
-  *reinterpret_cast<uint4*>(tile + (c0 >> 6) * HALF_BYTES + sw128_offset(r, (c0 & 63) >> 3)) = v;
-}
 
 struct AttnFwdParams {
   bf16* out; long long ldo;       // [B, Lq, ldo], head at column head*128
@@ -346,45 +325,6 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __r
   }
 }
 
-// K-major operand WITHOUT swizzle, 16 columns wide (one k-step): 8-row x 16-byte core matrices, the two 8-column
-// halves 128 B apart (LBO), consecutive 8-row groups 256 B apart (SBO).
-__device__ __forceinline__ uint64_t desc_k16_noswz(uint32_t addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(128 >> 4) << 16;
-  d |= static_cast<uint64_t>(256 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  return d;
-}
-__device__ __forceinline__ uint32_t k16_off(int row) { return (row >> 3) * 256 + (row & 7) * 16; }
-// x = hi + mid + lo with three bf16 terms (fp32-exact to ~2^-24 relative): the per-query statistics ride through
-// the tensor core as an extra rank-3 update instead of being re-read from shared memory for every element.
-__device__ __forceinline__ uint4 split3_bf16(float x) {
-  if (!(fabsf(x) < 3.0e38f)) return make_uint4(pack_bf16x2(x, 0.f), 0u, 0u, 0u);   // +-inf (masked query rows)
-  const float hi = bf16_round(x);
-  const float mid = bf16_round(x - hi);
-  const float lo = bf16_round(x - hi - mid);
-  return make_uint4(pack_bf16x2(hi, mid), pack_bf16x2(lo, 0.f), 0u, 0u);
-}
-
-struct AttnBwdParams {
-  const float* lse; const float* delta;   // [B, nh, Lq]
-  float* dq_acc; long long lddq;           // fp32 [B, Lq, lddq] (+=)
-  bf16* dk; long long lddk;                // bf16 [B, Lk, lddk], head at head*128 (q_splits == 1)
-  bf16* dv; long long lddv;
-  float* dk_acc; float* dv_acc; long long ldkv_acc;  // fp32 accumulation targets when q_splits > 1
-  float* compact_acc;   // q_splits > 1: [item - item_base][dk|dv][128][128] fp32 (tail balancing), overrides dk_acc/dv_acc
-  int item_base, kv_tiles;
-  int Lq, Lk, nh, q_splits;
-  float scale_log2, scale;
-  long long* dbg;   // optional per-iteration clock64 trace of CTA (0,0,0): [iter][8] (debug / tuning only)
-};
-#define VDS_TRACE(slot, it)                                                                      \
-  do {                                                                                           \
-    if (p.dbg != nullptr && blockIdx.x == 0 && (it) < 160)                                       \
-      p.dbg[(it) * 8 + (slot)] = clock64();                                                      \
-  } while (0)
-
 // Backward.  CTA = one 128-row K/V tile of one (b, head), looping over 64-row query sub-tiles:
 //   S^T = K Q^T (double-buffered), dP^T = V dO^T (single buffer)   TMEM   M=128 (kv) N=64 (q)  K=128 (d)
 //   P^T, dS^T -> bf16 into the retired S^T columns (A operands of dV / dK); dS^T also -> smem (B operand of dQ^T)
@@ -397,7 +337,6 @@ struct AttnBwdParams {
 // ~288 KiB of shared-memory traffic per sub-tile (operands 176, Q/dO fill 32, dS^T 16, dQ staging 2 x 32): the kernel
 // runs at ~90% of the shared-memory port, which is what bounds it.
 constexpr int BWD_THREADS = 384;
-constexpr int QSUB = 64;
 constexpr int QT_BYTES = QSUB * HD * 2;          // 16 KiB: 64 x 128 bf16 (two [64 x 128 B] halves)
 constexpr int QT_HALF = QT_BYTES / 2;            // 8 KiB
 constexpr int PT_BYTES = 128 * QSUB * 2;         // 16 KiB: [128 kv rows x 128 B]
@@ -431,10 +370,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + BWD_OFF_BAR + 112);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // 1-D grid over (item, split); item = (b * nh + head) * kv_tiles + kv_tile
-  const int item = p.item_base + blockIdx.x / p.q_splits, split = blockIdx.x % p.q_splits;
-  const int kv_tile = item % p.kv_tiles;
-  const int head = (item / p.kv_tiles) % p.nh, b = item / (p.kv_tiles * p.nh);
+  // 1-D grid over (local item, split); local item -> (b, head, kv tile) through attn_bwd_decode_item
+  const int item_local = blockIdx.x / p.q_splits, split = blockIdx.x % p.q_splits;
+  int kv_tile, head, b;
+  attn_bwd_decode_item(p, item_local, b, head, kv_tile);
   const int kv0 = kv_tile * 128;
   const int n_q_all = (p.Lq + QSUB - 1) / QSUB;
   const int per = (n_q_all + p.q_splits - 1) / p.q_splits;
@@ -742,7 +681,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
           } else {
             float* dst = p.compact_acc != nullptr
-                             ? p.compact_acc + ((long long)(item - p.item_base) * 2 + which) * (128 * HD) + r * HD + c * 32
+                             ? p.compact_acc + ((long long)item_local * 2 + which) * (128 * HD) + r * HD + c * 32
                              : (which == 0 ? p.dk_acc : p.dv_acc) + ((long long)b * p.Lk + krow) * p.ldkv_acc +
                                    head * HD + c * 32;
 #pragma unroll
@@ -762,15 +701,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 long long* g_attn_bwd_trace = nullptr;   // set through vds_debug_attn_bwd_trace (tuning only)
+int g_attn_pair_mode = -1;               // vds_debug_attn_pair_mode: -1 = VDS_ATTN_PAIR env (default auto), 0 off, 1 auto, 2 force
+
+int launch_attn_bwd_pairs(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
+                          int64_t lddo, const AttnBwdParams& p0, int B, int nh, int Lq, int Lk, int pair_base, int n_pairs,
+                          int pairs_per_bh, cudaStream_t stream);   // attention_bwd2.cu
 
 // tail balancing fix-up: compact fp32 [item][dk|dv][128][128] -> bf16 dk / dv tiles
 __global__ void __launch_bounds__(256) attn_bwd_tail_fixup_kernel(const float* __restrict__ compact, bf16* __restrict__ dk,
                                                                   long long lddk, bf16* __restrict__ dv, long long lddv,
-                                                                  int item_base, int kv_tiles, int nh, int Lk) {
+                                                                  const AttnBwdParams p, int Lk) {
   pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
   pdl_trigger();
-  const int item = item_base + blockIdx.x;
-  const int kv_tile = item % kv_tiles, head = (item / kv_tiles) % nh, b = item / (kv_tiles * nh);
+  int kv_tile, head, b;
+  attn_bwd_decode_item(p, blockIdx.x, b, head, kv_tile);
   const float* src = compact + (long long)blockIdx.x * 2 * 128 * HD;
   for (int idx = threadIdx.x; idx < 2 * 128 * (HD / 8); idx += blockDim.x) {
     const int which = idx / (128 * (HD / 8));
@@ -787,20 +731,6 @@ __global__ void __launch_bounds__(256) attn_bwd_tail_fixup_kernel(const float* _
   }
 }
 
-static int make_tmap_tokens(CUtensorMap* tm, const void* ptr, long long ld, int L, int nh, int B, int box_rows = 128) {
-  uint64_t dims[4] = {(uint64_t)HD, (uint64_t)L, (uint64_t)nh, (uint64_t)B};
-  uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)HD * 2, (uint64_t)L * (uint64_t)ld * 2};
-  uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
-  return encode_tmap_bf16(tm, ptr, 4, dims, strides, box);
-}
-// fp32 [B, L, ld] accumulation buffer, box = one [64 rows x 128 floats] sub-tile of one head, no swizzle
-static int make_tmap_dq(CUtensorMap* tm, const float* ptr, long long ld, int L, int nh, int B) {
-  uint64_t dims[4] = {(uint64_t)HD, (uint64_t)L, (uint64_t)nh, (uint64_t)B};
-  uint64_t strides[3] = {(uint64_t)ld * 4, (uint64_t)HD * 4, (uint64_t)L * (uint64_t)ld * 4};
-  uint32_t box[4] = {(uint32_t)HD, (uint32_t)QSUB, 1, 1};
-  return encode_tmap(tm, ptr, 1, 4, dims, strides, box, 0);
-}
-
 }  // namespace vds
 
 using namespace vds;
@@ -810,6 +740,13 @@ extern "C" {
 /* tuning aid: when non-NULL, CTA (0,0,0) of every following attn_bwd launch writes clock64 stamps [iter][8] here */
 int vds_debug_attn_bwd_trace(void* buf) {
   vds::g_attn_bwd_trace = (long long*)buf;
+  return VDS_OK;
+}
+
+/* tests / tuning: selects the backward kernel for self-attention-sized problems. -1: VDS_ATTN_PAIR env (default: auto),
+ * 0: 1-CTA kernel only, 1: auto (CTA-pair kernel for whole waves of kv-tile pairs), 2: CTA-pair kernel for every pair */
+int vds_debug_attn_pair_mode(int mode) {
+  vds::g_attn_pair_mode = mode;
   return VDS_OK;
 }
 
@@ -841,7 +778,7 @@ int vds_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
 
 int64_t vds_attn_bwd_tail_ws_bytes(int B, int nh, int Lk) {
   (void)B; (void)nh; (void)Lk;
-  return (int64_t)(num_sms() - 1) * 2 * 128 * HD * 4;   // at most SMs-1 remainder items
+  return (int64_t)(2 * num_sms()) * 2 * 128 * HD * 4;   // remainder items: < SMs tiles of the last wave of pairs + one unpaired tile per (b, head), capped
 }
 
 /* delta = rowsum(dO * O) (computed here from o, or passed in precomputed when o == NULL); dq_acc must be zero-initialised fp32 [B, Lq, lddq]; with q_splits > 1 dk/dv are
@@ -882,37 +819,85 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.dbg = g_attn_bwd_trace;
   p.compact_acc = nullptr;
+  p.rem_pair_base = -1; p.rem_pairs_per_bh = 1; p.rem_pair_tiles = 0;
   const int kv_tiles = (Lk + 127) / 128;
   p.kv_tiles = kv_tiles;
+  p.item_base = 0;
   const int total = kv_tiles * nh * B;
-  // Tail balancing: with one CTA per (kv tile, head, batch) the last wave of the grid is partly empty (520 items on 148
-  // SMs = 3.51 waves cost 4).  The remainder items are split `s` ways along the query range in a second launch (fp32
-  // red into a compact workspace + a bf16 fix-up), so the tail costs ceil(rem*s/SMs)/s waves instead of 1.
-  int tail_s = 0;
   const int sms = num_sms();
-  const int full = (total / sms) * sms, rem = total - full;
-  if (q_splits == 1 && tail_ws != nullptr && full > 0 && rem > 0 && (Lq + QSUB - 1) / QSUB >= 32) {
-    double best = 1.0;
-    for (int s = 2; s <= 8; ++s) {
-      const double cost = (double)((rem * s + sms - 1) / sms) / s + 0.02 * s;   // + per-split prologue / atomics
-      if (cost < best - 0.1 && (long long)rem * 2 * 128 * HD * 4 <= tail_ws_bytes) { best = cost; tail_s = s; }
+  const int n_qsub = (Lq + QSUB - 1) / QSUB;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  // `rem` items (local indices 0..rem-1 under the indexing already set in p) on the 1-CTA kernel.  With a workspace and
+  // a long query range they are split `s` ways along the query range (fp32 red into a compact workspace + a bf16
+  // fix-up), so a partly filled last wave costs ceil(rem*s/SMs)/s waves instead of 1.
+  auto launch_items = [&](int rem, bool allow_split) -> int {
+    int tail_s = 0;
+    if (allow_split && tail_ws != nullptr && rem > 0 && rem % sms != 0 && n_qsub >= 32 &&
+        (long long)rem * 2 * 128 * HD * 4 <= tail_ws_bytes) {
+      double best = (double)((rem + sms - 1) / sms);
+      for (int s = 2; s <= 8; ++s) {
+        const double cost = (double)((rem * s + sms - 1) / sms) / s + 0.02 * s;   // + per-split prologue / atomics
+        if (cost < best - 0.1) { best = cost; tail_s = s; }
+      }
     }
+    if (tail_s == 0) {
+      if (p.rem_pair_base >= 0) p.dbg = nullptr;
+      launch_k(attn_bwd_kernel, rem * p.q_splits, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, tdq, p);
+      VDS_CHECK_LAUNCH("attn_bwd");
+      return VDS_OK;
+    }
+    cudaMemsetAsync(tail_ws, 0, (size_t)rem * 2 * 128 * HD * 4, st);
+    AttnBwdParams ps = p;
+    ps.q_splits = tail_s; ps.compact_acc = (float*)tail_ws;
+    if (p.rem_pair_base >= 0) ps.dbg = nullptr;   // the trace buffer belongs to the pair kernel of this call
+    launch_k(attn_bwd_kernel, rem * tail_s, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, tdq, ps);
+    VDS_CHECK_LAUNCH("attn_bwd");
+    launch_k(attn_bwd_tail_fixup_kernel, rem, 256, 0, st, (const float*)tail_ws, (bf16*)dk, lddk, (bf16*)dv, lddv, ps, Lk);
+    VDS_CHECK_LAUNCH("attn_bwd_tail_fixup");
+    return VDS_OK;
+  };
+
+  // CTA-pair kernel (attention_bwd2.cu) for the bulk of a self-attention-sized problem: whole waves of kv-tile pairs
+  // (2 adjacent tiles of one (b, head) per 2-CTA cluster); what is left — the pairs of the last, partly filled wave and
+  // the unpaired last tile when kv_tiles is odd — goes to the 1-CTA kernel with query-range splits.
+  // VDS_ATTN_PAIR=0 disables it, VDS_ATTN_PAIR=force uses it for every pair regardless of wave fill (tests).
+  int pair_mode = g_attn_pair_mode;
+  if (pair_mode < 0) {
+    static int env_mode = -1;
+    if (env_mode < 0) {
+      const char* e = getenv("VDS_ATTN_PAIR");
+      env_mode = (e == nullptr) ? 1 : (strcmp(e, "0") == 0 ? 0 : (strcmp(e, "force") == 0 ? 2 : 1));
+    }
+    pair_mode = env_mode;
   }
-  if (tail_s == 0) {
-    p.item_base = 0;
-    launch_k(attn_bwd_kernel, total * q_splits, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream, tq, tk, tv, tdo, tdq, p);
+  const int pairs_per_bh = kv_tiles / 2;
+  const int total_pairs = pairs_per_bh * nh * B;
+  const int clusters = sms / 2;
+  int pairs_main = 0;
+  if (pair_mode != 0 && q_splits == 1 && dk != nullptr && dv != nullptr) {
+    if (pair_mode == 2) pairs_main = total_pairs;
+    else if (n_qsub >= 32) pairs_main = (total_pairs / clusters) * clusters;
+  }
+  if (pairs_main > 0) {
+    if ((r = launch_attn_bwd_pairs(q, ldq, k, ldk, v, ldv, d_o, lddo, p, B, nh, Lq, Lk, 0, pairs_main, pairs_per_bh, st)))
+      return r;
+    p.rem_pair_base = pairs_main;
+    p.rem_pairs_per_bh = pairs_per_bh;
+    p.rem_pair_tiles = 2 * (total_pairs - pairs_main);
+    const int rem = p.rem_pair_tiles + ((kv_tiles & 1) ? nh * B : 0);
+    if (rem > 0 && (r = launch_items(rem, true))) return r;
+    return VDS_OK;
+  }
+  // 1-CTA kernel for everything: full waves in one launch, the remainder of the last wave split along the query range
+  const int full = (total / sms) * sms, rem = total - full;
+  if (q_splits == 1 && tail_ws != nullptr && full > 0 && rem > 0 && n_qsub >= 32) {
+    if ((r = launch_items(full, false))) return r;
+    p.item_base = full;
+    if ((r = launch_items(rem, true))) return r;
   } else {
-    p.item_base = 0;
-    launch_k(attn_bwd_kernel, full, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream, tq, tk, tv, tdo, tdq, p);
-    VDS_CHECK_LAUNCH("attn_bwd");
-    cudaMemsetAsync(tail_ws, 0, (size_t)rem * 2 * 128 * HD * 4, (cudaStream_t)stream);
-    p.item_base = full; p.q_splits = tail_s; p.compact_acc = (float*)tail_ws;
-    launch_k(attn_bwd_kernel, rem * tail_s, BWD_THREADS, BWD_SMEM, (cudaStream_t)stream, tq, tk, tv, tdo, tdq, p);
-    VDS_CHECK_LAUNCH("attn_bwd");
-    launch_k(attn_bwd_tail_fixup_kernel, rem, 256, 0, (cudaStream_t)stream, (const float*)tail_ws, (bf16*)dk, lddk, (bf16*)dv,
-                                                                      lddv, full, kv_tiles, nh, Lk);
+    if ((r = launch_items(total, false))) return r;
   }
-  VDS_CHECK_LAUNCH("attn_bwd");
   return VDS_OK;
 }
 

@@ -1,0 +1,582 @@
+// Attention backward on CTA PAIRS (tcgen05.mma.cta_group::2 + distributed shared memory), head_dim = 128
+// (autograd of model.py:136; the 1-CTA kernel in attention.cu keeps cross-attention, query-range splits and tails).
+//
+// Why pairs.  The 1-CTA kernel is bound by its shared-memory port (~288 KiB per 64-row query sub-tile).
+// A cluster of two CTAs owns two adjacent 128-row K/V tiles of one (b, head) and walks the query range together:
+//   S^T  = K Q^T , dP^T = V dO^T     M = 256 (kv rows of both CTAs) x N = 64 (q) x K = 128 (d)
+//   dV  += P^T dO, dK  += dS^T Q     M = 256 x N = 128 (d) x K = 64 (q), A = P^T / dS^T (bf16) from TMEM
+//        every CTA feeds its own 128 rows of A and only HALF of each B operand (32 query rows, resp. 64 of the 128
+//        d columns), so the Q / dO operand reads and fills per CTA are halved;
+//   dQ^T = K^T dS^T                   M = 128 (d: 64 per CTA) x N = 64 (q) x K = 256 (kv rows of BOTH tiles)
+//        the contraction runs over the pair's 256 kv rows, so each CTA ends up with a fully pair-summed 64 (d) x 64 (q)
+//        block: half the fp32 staging traffic and half the TMA reductions into the fp32 dq buffer.  Its B operand —
+//        dS^T of all 256 kv rows for this CTA's 32 query columns — is assembled by the compute warps of both CTAs: every
+//        thread (= one kv row) stores one 64-byte half row locally and the other half into the peer's shared memory
+//        (st.shared::cluster), then fence.proxy.async + a release.cluster arrive on the leader's barrier.
+// Per CTA and sub-tile that is ~224 KiB through the shared-memory port instead of ~288 KiB and ~1560 tensor-pipe cycles
+// instead of ~1840 (scripts/mma_shapes2.cu: M256 N64 SS 40-50 cycles for the pair against 53 per CTA; M128 N64 22-28).
+// The operand / accumulator layouts of the three cta_group::2 shapes (N-split B halves, the 128-lane x 32-column TMEM
+// image of the M128 accumulator, the 64-byte-swizzle MN-major B tile, remote stores feeding the async proxy) were pinned
+// on the hardware with scripts/umma_probe.py before this kernel was written.
+//
+// Roles per CTA (384 threads): warp 0 TMA producer | warp 1 MMA issuer (leader CTA only) | warps 4-7 compute
+// (thread == kv row) | warps 8-11 dQ drain.  All MMA-completion signals are commits multicast to both CTAs' barriers;
+// everything the issuer waits for arrives on the LEADER's barriers (remote arrives from the follower).
+#include <cuda.h>
+
+#include "attn_common.cuh"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vds {
+
+constexpr int B2_THREADS = 384;
+constexpr int B2_OFF_K = 0;                               // own K tile, K-major SW128, two 64-wide d halves      32 KiB
+constexpr int B2_OFF_V = B2_OFF_K + TILE_BYTES;           // own V tile                                             32 KiB
+constexpr int B2_OFF_KT = B2_OFF_V + TILE_BYTES;          // [kv tile 0 | 1] x [128 kv x 64 d of THIS CTA's d half]  32 KiB
+constexpr int B2_ROWS_STAGE = 16384;                      // Q rows-half 2 x [32 x 128 B] | dO rows-half
+constexpr int B2_OFF_ROWS = B2_OFF_KT + TILE_BYTES;       // 2 stages                                               32 KiB
+constexpr int B2_COLS_STAGE = 16384;                      // Q cols-half [64 q x 128 B] | dO cols-half
+constexpr int B2_OFF_COLS = B2_OFF_ROWS + 2 * B2_ROWS_STAGE;   // 2 stages                                          32 KiB
+constexpr int B2_OFF_ONES = B2_OFF_COLS + 2 * B2_COLS_STAGE;   // ones tile [128 x 16] no swizzle                    4 KiB
+constexpr int B2_OFF_STAT = B2_OFF_ONES + 4096;           // [buf 0|1][lse | delta] x [32 q x 16] no swizzle          4 KiB
+constexpr int B2_OFF_DS = B2_OFF_STAT + 4096;             // [kv tile 0 | 1] x [128 kv x 32 q] bf16, 64-byte swizzle  16 KiB
+constexpr int B2_OFF_STG = B2_OFF_DS + 16384;             // fp32 [64 q][64 d] staging of the dQ block               16 KiB
+constexpr int B2_OFF_SEND = B2_OFF_STG + 16384;           // this kv tile's dS^T half for the PEER (bulk-copied over DSMEM)  8 KiB
+constexpr int B2_OFF_BAR = B2_OFF_SEND + 8192;
+constexpr int B2_SMEM = B2_OFF_BAR + 256 + 1024;
+
+__device__ __forceinline__ uint32_t mapa_cta(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+// Arrive on a barrier of (possibly) another CTA of the cluster.  What these arrivals publish lives in TMEM (ordered by
+// tcgen05.fence::before_thread_sync) or in this CTA's own shared memory behind fence.proxy.async, so the default
+// .release.cta form is used: a .release.cluster arrive costs a cluster-scope memory barrier (measured: it and the generic
+// fence.proxy.async after remote stores made the compute warps' hand-off ~3000 cycles per sub-tile).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// shared::cta -> peer shared memory bulk copy (async proxy on both sides); completes `bytes` on the PEER's barrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t peer_dst, uint32_t src, uint32_t bytes, uint32_t peer_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(peer_dst),
+               "r"(src), "r"(bytes), "r"(peer_bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const void* tmap, uint32_t leader_bar, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// all MMAs issued so far by this thread arrive on the barrier at this offset in BOTH CTAs when complete
+__device__ __forceinline__ void commit2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// MN-major B tile with 32 elements (64 bytes) per k row, 64-byte swizzle: 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t desc_mn_sw64(uint32_t addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(2048 >> 4) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+// byte offset of 16-byte chunk c (0..3) of row r in a [rows x 64 B] tile with the 64-byte swizzle
+__device__ __forceinline__ uint32_t sw64_offset(uint32_t r, uint32_t c) { return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4); }
+
+// tuning aid: cluster 0 stamps clock64 per sub-tile: dbg[cta][iter][16]
+#define B2_TRACE(slot, it)                                                                              \
+  do {                                                                                                  \
+    if (p.dbg != nullptr && blockIdx.x < 2 && (it) < 160)                                               \
+      p.dbg[((long long)crank * 160 + (it)) * 16 + (slot)] = clock64();                                 \
+  } while (0)
+
+struct AttnBwd2Params {
+  AttnBwdParams p;
+  int pair_base, pairs_per_bh;   // this launch covers pairs [pair_base, pair_base + gridDim.x / 2); pair -> (b*nh + head, kv tiles 2j, 2j+1)
+};
+
+__global__ void __launch_bounds__(B2_THREADS, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQr,
+                 const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                 const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDOr,
+                 const __grid_constant__ CUtensorMap tmDQ, const AttnBwd2Params pp) {
+  const AttnBwdParams& p = pp.p;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw_addr);
+  const uint32_t sK = base + B2_OFF_K, sV = base + B2_OFF_V, sKT = base + B2_OFF_KT, sROWS = base + B2_OFF_ROWS,
+                 sCOLS = base + B2_OFF_COLS, sONES = base + B2_OFF_ONES, sSTAT = base + B2_OFF_STAT, sDS = base + B2_OFF_DS,
+                 sSTG = base + B2_OFF_STG, sSEND = base + B2_OFF_SEND;
+  uint8_t* gONES = gen + B2_OFF_ONES;
+  uint8_t* gSTAT = gen + B2_OFF_STAT;
+  uint8_t* gDS = gen + B2_OFF_DS;
+  uint8_t* gSEND = gen + B2_OFF_SEND;
+  float* gSTG = reinterpret_cast<float*>(gen + B2_OFF_STG);
+  const uint32_t bars = base + B2_OFF_BAR;
+  // barriers that live (are waited on) in the LEADER only: *_full of the TMA rings, and everything the issuer waits for
+  const uint32_t kv_full = bars, rows_full = bars + 8, cols_full = bars + 24, stat_full = bars + 40, dp_read = bars + 56,
+                 pds_full = bars + 64, dq_drained = bars + 72;
+  // barriers every CTA waits on locally (multicast commits of the leader's MMAs)
+  const uint32_t rows_empty = bars + 80, cols_empty = bars + 96, s_full = bars + 112, dp_full = bars + 128,
+                 dq_full = bars + 136, mma_done = bars + 144, tmem_slot = bars + 160;
+  // dS^T exchange: ds_in (every CTA's own) completes when the peer's 8 KiB half has landed in this CTA's sDS;
+  // ds1_ready (leader's) is the follower's relay of its ds_in
+  const uint32_t ds_in = bars + 168, ds1_ready = bars + 176;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + B2_OFF_BAR + 160);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int pid = pp.pair_base + (blockIdx.x >> 1);
+  const int bh = pid / pp.pairs_per_bh, pj = pid % pp.pairs_per_bh;
+  const int head = bh % p.nh, b = bh / p.nh;
+  const int kv0_pair = pj * 256, kv0 = kv0_pair + (int)crank * 128;
+  const int n_q = (p.Lq + QSUB - 1) / QSUB;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 2);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(rows_full + 8 * s, 2);
+      mbar_init(cols_full + 8 * s, 2);
+      mbar_init(stat_full + 8 * s, 8);     // 4 compute warps x 2 CTAs
+      mbar_init(rows_empty + 8 * s, 1);
+      mbar_init(cols_empty + 8 * s, 1);
+      mbar_init(s_full + 8 * s, 1);
+      mbar_init(mma_done + 8 * s, 1);
+    }
+    mbar_init(dp_read, 8);
+    mbar_init(pds_full, 8);
+    mbar_init(dq_drained, 8);                // 4 drain warps x 2 CTAs
+    mbar_init(dp_full, 1);
+    mbar_init(dq_full, 1);
+    mbar_init(ds_in, 1);
+    mbar_init(ds1_ready, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmQr); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDOr); tma_prefetch_desc(&tmDQ);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();      // everything above is launch-independent set-up; global inputs may come from the previous kernel
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / multicast commit / 2-SM TMA
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+  // TMEM columns (same in both CTAs): dV [0,128) | dK [128,256) | S^T buffers [256,320) [320,384) (afterwards bf16 P^T in
+  // their columns 0..31 and dS^T in 32..63) | dP^T [384,448) | dQ^T [448,480): 128 lanes x 32 columns, lane % 64 = d of
+  // this CTA's half, lane / 64 = which 32 query columns
+  const uint32_t tDV = tmem, tDK = tmem + 128, tSTb = tmem + 256, tDPTs = tmem + 384, tDQT = tmem + 448;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs, own operand halves)
+    if (lane == 0) {
+      auto lbar = [&](uint32_t bar) { return mapa_cta(bar, 0); };
+      auto arm = [&](uint32_t bar, uint32_t bytes_both) {   // leader: expect both CTAs' bytes; follower: plain arrive
+        if (leader) mbar_expect_tx(bar, bytes_both);
+        else mbar_arrive_remote(lbar(bar));
+      };
+      arm(kv_full, 2 * 3 * TILE_BYTES);
+      const uint32_t kvb = lbar(kv_full);
+      tma_load_4d_2sm(sK, &tmK, kvb, 0, kv0, head, b);
+      tma_load_4d_2sm(sK + HALF_BYTES, &tmK, kvb, 64, kv0, head, b);
+      tma_load_4d_2sm(sV, &tmV, kvb, 0, kv0, head, b);
+      tma_load_4d_2sm(sV + HALF_BYTES, &tmV, kvb, 64, kv0, head, b);
+      tma_load_4d_2sm(sKT, &tmK, kvb, (int)crank * 64, kv0_pair, head, b);                 // K of tile 0, my d half
+      tma_load_4d_2sm(sKT + HALF_BYTES, &tmK, kvb, (int)crank * 64, kv0_pair + 128, head, b);   // K of tile 1, my d half
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i & 1;
+        const uint32_t us = (i >> 1) & 1;
+        const int q0 = i * QSUB;
+        {
+          mbar_wait(rows_empty + 8 * st, us ^ 1u);
+          arm(rows_full + 8 * st, 2 * B2_ROWS_STAGE);
+          const uint32_t fb = lbar(rows_full + 8 * st);
+          const uint32_t dq = sROWS + st * B2_ROWS_STAGE, dd = dq + 8192;
+          const int row0 = q0 + (int)crank * 32;
+          tma_load_4d_2sm(dq, &tmQr, fb, 0, row0, head, b);
+          tma_load_4d_2sm(dq + 4096, &tmQr, fb, 64, row0, head, b);
+          tma_load_4d_2sm(dd, &tmDOr, fb, 0, row0, head, b);
+          tma_load_4d_2sm(dd + 4096, &tmDOr, fb, 64, row0, head, b);
+        }
+        {
+          mbar_wait(cols_empty + 8 * st, us ^ 1u);
+          arm(cols_full + 8 * st, 2 * B2_COLS_STAGE);
+          const uint32_t fb = lbar(cols_full + 8 * st);
+          const uint32_t dq = sCOLS + st * B2_COLS_STAGE, dd = dq + 8192;
+          tma_load_4d_2sm(dq, &tmQ, fb, (int)crank * 64, q0, head, b);
+          tma_load_4d_2sm(dd, &tmDO, fb, (int)crank * 64, q0, head, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(256, 64, false, false);     // S^T, dP^T
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(256, 128, false, true);   // dV, dK
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, true, true);      // dQ^T (64 rows of d per CTA)
+      auto issue_s = [&](int k) {
+        const int bb = k & 1;
+        if (lane == 0) B2_TRACE(0, k);    // S(k): start waiting
+        mbar_wait(rows_full + 8 * bb, (k >> 1) & 1);
+        if (lane == 0) B2_TRACE(1, k);    // rows landed
+        mbar_wait(stat_full + 8 * bb, (k >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) B2_TRACE(2, k);    // stats ready: issue
+        if (elect_one()) {
+          const uint32_t q = sROWS + bb * B2_ROWS_STAGE;
+          const uint32_t tST = tSTb + bb * 64;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            mma2_ss(tST, desc_kmajor(sK, kk), umma_smem_desc(q + (kk >> 2) * 4096 + (kk & 3) * 32, 16, 1024), idesc_s, kk > 0);
+          mma2_ss(tST, desc_k16_noswz(sONES), desc_k16_noswz(sSTAT + (bb * 2 + 0) * 1024), idesc_s, 1);   // - lse
+          commit2(s_full + 8 * bb);
+        }
+        __syncwarp();
+      };
+      auto issue_dp = [&](int k) {
+        const int bb = k & 1;
+        if (lane == 0) B2_TRACE(3, k);    // S(k) issued, waiting for dp_read
+        if (k > 0) mbar_wait(dp_read, (k - 1) & 1);
+        tc_fence_after();
+        if (lane == 0) B2_TRACE(4, k);    // dP(k) issue
+        if (elect_one()) {
+          const uint32_t d_o = sROWS + bb * B2_ROWS_STAGE + 8192;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            mma2_ss(tDPTs, desc_kmajor(sV, kk), umma_smem_desc(d_o + (kk >> 2) * 4096 + (kk & 3) * 32, 16, 1024), idesc_s,
+                    kk > 0);
+          mma2_ss(tDPTs, desc_k16_noswz(sONES), desc_k16_noswz(sSTAT + (bb * 2 + 1) * 1024), idesc_s, 1);   // - delta
+          commit2(dp_full);
+          commit2(rows_empty + 8 * bb);   // both users of this rows stage (S^T, dP^T) are complete
+        }
+        __syncwarp();
+      };
+      mbar_wait(kv_full, 0);
+      issue_s(0);
+      issue_dp(0);
+      for (int i = 0; i < n_q; ++i) {
+        const int bb = i & 1;
+        if (i + 1 < n_q) {
+          issue_s(i + 1);
+          issue_dp(i + 1);
+        }
+        if (lane == 0) B2_TRACE(5, i);    // waiting for pds_full(i)
+        if (elect_one()) mbar_expect_tx(ds_in, 8192);   // the follower's dS^T half of sub-tile i lands in my sDS slot 1
+        __syncwarp();
+        mbar_wait(pds_full, i & 1);
+        mbar_wait(ds_in, i & 1);
+        mbar_wait(ds1_ready, i & 1);
+        if (lane == 0) B2_TRACE(6, i);
+        if (i > 0) mbar_wait(dq_drained, (i - 1) & 1);
+        if (lane == 0) B2_TRACE(7, i);
+        mbar_wait(cols_full + 8 * bb, (i >> 1) & 1);
+        tc_fence_after();
+        if (lane == 0) B2_TRACE(8, i);    // dQ/dV/dK(i) issue
+        if (elect_one()) {
+          const uint32_t q = sCOLS + bb * B2_COLS_STAGE, d_o = q + 8192;
+          const uint32_t tPT = tSTb + bb * 64;
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk)   // dQ^T over the 256 kv rows of the pair: tile kk >> 3, 16 rows per k-step
+            mma2_ss(tDQT, umma_smem_desc(sKT + (kk >> 3) * HALF_BYTES + (kk & 7) * 2048, 4096, 1024),
+                    desc_mn_sw64(sDS + (kk >> 3) * 8192 + (kk & 7) * 1024), idesc_dq, kk > 0);
+          commit2(dq_full);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)   // dV += P^T dO : B = this CTA's 64 d columns of dO, MN-major
+            mma2_ts(tDV, tPT + kk * 8, umma_smem_desc(d_o + kk * 2048, 8192, 1024), idesc_acc, (i > 0 || kk > 0));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)   // dK += dS^T Q
+            mma2_ts(tDK, tPT + 32 + kk * 8, umma_smem_desc(q + kk * 2048, 8192, 1024), idesc_acc, (i > 0 || kk > 0));
+          commit2(cols_empty + 8 * bb);
+          commit2(mma_done + 8 * bb);
+        }
+        __syncwarp();
+      }
+    } else {
+      // follower: relay "the leader's dS^T half has landed in my sDS slot 0" to the leader's issuer
+      const uint32_t l_ds1_ready = mapa_cta(ds1_ready, 0);
+      for (int i = 0; i < n_q; ++i) {
+        if (lane == 0) {
+          mbar_expect_tx(ds_in, 8192);
+          mbar_wait(ds_in, i & 1);
+          mbar_arrive_remote(l_ds1_ready);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ compute warpgroup (thread == kv row)
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int ct = threadIdx.x - 128;    // 0..127 == r
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const bool kv_ok = (kv0 + r) < p.Lk;
+    const bool kv_full_tile = kv0 + 128 <= p.Lk;
+    const long long stat_base = ((long long)b * p.nh + head) * p.Lq;
+    // statistics tile of this CTA: its 32 query rows of the sub-tile; threads 0..31 write -lse/scale, 32..63 -delta
+    const bool stat_thread = ct < 64;
+    const int which = (ct >> 5) & 1, srow = ct & 31;
+    const float* stat_src = (which == 0 ? p.lse : p.delta) + stat_base;
+    const float inv_sl2 = 1.0f / p.scale_log2;
+    const uint32_t l_stat_full = mapa_cta(stat_full, 0), l_dp_read = mapa_cta(dp_read, 0), l_pds_full = mapa_cta(pds_full, 0);
+    const uint32_t peer_ds = mapa_cta(sDS, crank ^ 1u), peer_ds_in = mapa_cta(ds_in, crank ^ 1u);
+    auto stat_fetch = [&](int k) -> float {
+      float raw = 0.f;
+      if (stat_thread) {
+        const int q = min(k * QSUB + (int)crank * 32 + srow, p.Lq - 1);
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(raw) : "l"(stat_src + q));
+      }
+      return raw;
+    };
+    auto stat_finish = [&](int k, float raw) -> float {
+      const int q = k * QSUB + (int)crank * 32 + srow;
+      if (q >= p.Lq) return which == 0 ? -INFINITY : 0.f;        // padded query row: exp2(-inf) = 0
+      return which == 0 ? -raw * inv_sl2 : -raw;
+    };
+    auto stat_write = [&](int k, float v) {
+      if (stat_thread) {
+        uint8_t* tile = gSTAT + ((k & 1) * 2 + which) * 1024;
+        *reinterpret_cast<uint4*>(tile + k16_off(srow)) = split3_bf16(v);
+        *reinterpret_cast<uint4*>(tile + k16_off(srow) + 128) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    auto arrive_leader = [&](uint32_t cluster_bar) {   // one arrival per warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(cluster_bar);
+    };
+    {  // constant A operand of the statistics k-step: ones in columns 0..2 of every kv row
+      const float one = 1.0f;
+      *reinterpret_cast<uint4*>(gONES + k16_off(ct)) = make_uint4(pack_bf16x2(one, one), pack_bf16x2(one, 0.f), 0u, 0u);
+      *reinterpret_cast<uint4*>(gONES + k16_off(ct) + 128) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int k = 0; k < 2 && k < n_q; ++k) {
+      stat_write(k, stat_finish(k, stat_fetch(k)));
+      fence_proxy_async_smem();
+      arrive_leader(l_stat_full + 8 * (k & 1));
+    }
+    for (int i = 0; i < n_q; ++i) {
+      const int bb = i & 1;
+      const float next_raw = (i + 2 < n_q) ? stat_fetch(i + 2) : 0.f;
+      mbar_wait(s_full + 8 * bb, (i >> 1) & 1);
+      tc_fence_after();
+      if (ct == 0) B2_TRACE(9, i);      // compute sees S(i)
+      const uint32_t tST = tSTb + bb * 64 + lane_off, tDPT = tDPTs + lane_off;
+      // phase 1 (overlaps the dQ/dV/dK MMAs of the previous sub-tile): p = exp2(s'), P^T -> TMEM
+      float pf[64];
+      {
+        uint32_t sv0[32], sv1[32];
+        tmem_ld32(tST, sv0);
+        tmem_ld32(tST + 32, sv1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          float p0 = ex2(__uint_as_float(sv0[e]) * p.scale_log2);
+          float p1 = ex2(__uint_as_float(sv1[e]) * p.scale_log2);
+          if (!kv_full_tile) {
+            p0 = kv_ok ? p0 : 0.f;
+            p1 = kv_ok ? p1 : 0.f;
+          }
+          pf[e] = p0;
+          pf[32 + e] = p1;
+        }
+      }
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) pk[e] = pack_bf16x2(pf[2 * e], pf[2 * e + 1]);
+        tmem_st32(tST, pk);
+      }
+      // phase 2: dS^T = P^T o dP'^T * scale once dP^T(i) has landed
+      if (ct == 0) B2_TRACE(10, i);     // exp done, waiting for dP(i)
+      mbar_wait(dp_full, i & 1);
+      tc_fence_after();
+      if (ct == 0) B2_TRACE(11, i);
+      uint32_t dd[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t dv[32];
+        tmem_ld32(tDPT + c * 32, dv);
+        tmem_ld_wait();
+        if (c == 1) {   // dP^T(i) is in registers: the issuer may refill the buffer with dP^T(i+1)
+          tc_fence_before();
+          arrive_leader(l_dp_read);
+        }
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const float d0 = pf[c * 32 + e] * (__uint_as_float(dv[e]) * p.scale);
+          const float d1 = pf[c * 32 + e + 1] * (__uint_as_float(dv[e + 1]) * p.scale);
+          dd[c * 16 + (e >> 1)] = pack_bf16x2(d0, d1);
+        }
+      }
+      tmem_st32(tST + 32, dd);
+      if (ct == 0) B2_TRACE(12, i);     // math done
+      if (i > 0) mbar_wait(dq_full, (i - 1) & 1);   // dS^T tiles of BOTH CTAs consumed by dQ^T(i-1)
+      if (ct == 0) B2_TRACE(13, i);
+      // dS^T row of this kv row: query columns 0..31 belong to CTA 0's B tile, 32..63 to CTA 1's; slot = my kv tile.
+      // My half goes straight into my sDS, the peer's half into the send buffer (same 64-byte-swizzle image), which one
+      // bulk DSMEM copy moves into the peer's sDS (async proxy on both ends: no remote generic stores, no cluster fence).
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t off = sw64_offset(r, c);
+        const uint4 h0 = make_uint4(dd[c * 4], dd[c * 4 + 1], dd[c * 4 + 2], dd[c * 4 + 3]);                  // q 0..31
+        const uint4 h1 = make_uint4(dd[16 + c * 4], dd[16 + c * 4 + 1], dd[16 + c * 4 + 2], dd[16 + c * 4 + 3]);   // q 32..63
+        *reinterpret_cast<uint4*>(gDS + crank * 8192u + off) = leader ? h0 : h1;
+        *reinterpret_cast<uint4*>(gSEND + off) = leader ? h1 : h0;
+      }
+      // statistics tile of sub-tile i+2 (buffer bb: S^T(i) and dP^T(i), its readers, are complete) shares the fence
+      if (i + 2 < n_q) stat_write(i + 2, stat_finish(i + 2, next_raw));
+      tmem_st_wait();
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(3, 128);            // every row of the send buffer is written and fenced
+      if (ct == 0) dsmem_bulk_copy(peer_ds + crank * 8192u, sSEND, 8192, peer_ds_in);
+      arrive_leader(l_pds_full);
+      if (i + 2 < n_q) arrive_leader(l_stat_full + 8 * bb);
+      if (ct == 0) B2_TRACE(14, i);     // pds arrive
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ dQ drain warpgroup
+    const int quad = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int d_local = (quad & 1) * 32 + lane;   // TMEM lane % 64
+    const int qh = quad >> 1;                      // TMEM lane / 64: query columns qh*32 ..
+    const bool lead_thread = threadIdx.x == 256;
+    const uint32_t l_dq_drained = mapa_cta(dq_drained, 0);
+    for (int i = 0; i < n_q; ++i) {
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tDQT + lane_off, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(l_dq_drained);
+      if (lead_thread) B2_TRACE(15, i);  // drain: dQ(i) in registers
+      if (lead_thread) bulk_wait_group_read0();      // previous reduction has finished reading the staging tile
+      named_bar_sync(2, 128);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) gSTG[(qh * 32 + c) * 64 + d_local] = __uint_as_float(v[c]);
+      fence_proxy_async_smem();
+      named_bar_sync(2, 128);
+      if (lead_thread) {
+        tma_reduce_add_4d(&tmDQ, sSTG, (int)crank * 64, i * QSUB, head, b);
+        bulk_commit_group();
+      }
+    }
+    if (lead_thread) bulk_wait_group0();
+  }
+  if (warp >= 4) {
+    // dK (compute warpgroup) / dV (drain warpgroup) of this CTA's own kv rows: TMEM lane == kv row
+    const int which = warp >= 8 ? 1 : 0;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    mbar_wait(mma_done + 8 * ((n_q - 1) & 1), ((n_q - 1) >> 1) & 1);
+    tc_fence_after();
+    const int krow = kv0 + r;
+    const uint32_t t = (which == 0 ? tDK : tDV) + lane_off;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t + c * 32, v);
+      tmem_ld_wait();
+      if (krow < p.Lk) {
+        bf16* dst = (which == 0 ? p.dk + ((long long)b * p.Lk + krow) * p.lddk
+                                : p.dv + ((long long)b * p.Lk + krow) * p.lddv) + head * HD + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+          u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+          u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+          u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + g * 8) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // nobody leaves while the peer may still store into / arrive on / multicast to this CTA
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// Launches the pair kernel on pairs [pair_base, pair_base + n_pairs) of the (b, head, kv-tile-pair) space.
+int launch_attn_bwd_pairs(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
+                          int64_t lddo, const AttnBwdParams& p0, int B, int nh, int Lq, int Lk, int pair_base, int n_pairs,
+                          int pairs_per_bh, cudaStream_t stream) {
+  CUtensorMap tq, tqr, tk, tv, tdo, tdor, tdq;
+  int r;
+  if ((r = make_tmap_tokens(&tq, q, ldq, Lq, nh, B, QSUB))) return r;
+  if ((r = make_tmap_tokens(&tqr, q, ldq, Lq, nh, B, 32))) return r;
+  if ((r = make_tmap_tokens(&tk, k, ldk, Lk, nh, B))) return r;
+  if ((r = make_tmap_tokens(&tv, v, ldv, Lk, nh, B))) return r;
+  if ((r = make_tmap_tokens(&tdo, d_o, lddo, Lq, nh, B, QSUB))) return r;
+  if ((r = make_tmap_tokens(&tdor, d_o, lddo, Lq, nh, B, 32))) return r;
+  if ((r = make_tmap_dq(&tdq, p0.dq_acc, p0.lddq, Lq, nh, B, 64))) return r;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
+    if (e != cudaSuccess) { set_error("attn_bwd2: smem attribute: %s", cudaGetErrorString(e)); return VDS_ERR_CUDA; }
+    attr = true;
+  }
+  AttnBwd2Params pp;
+  pp.p = p0;
+  pp.pair_base = pair_base;
+  pp.pairs_per_bh = pairs_per_bh;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * n_pairs);
+  cfg.blockDim = dim3(B2_THREADS);
+  cfg.dynamicSmemBytes = B2_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = 2;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see common.h: launch_k
+  attrs[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_bwd2_kernel, tq, tqr, tk, tv, tdo, tdor, tdq, pp);
+  if (e != cudaSuccess) {
+    set_error("attn_bwd2: cluster launch failed: %s", cudaGetErrorString(e));
+    return VDS_ERR_CUDA;
+  }
+  VDS_CHECK_LAUNCH("attn_bwd2");
+  return VDS_OK;
+}
+
+}  // namespace vds

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "vds_attn_bwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp, i64, vp, vp,
                      i64, i32, i32, i32, i32, i32, i32, f32, vp, i64, vp],
     "vds_debug_attn_bwd_trace": [vp],
+    "vds_debug_attn_pair_mode": [i32],
     "vds_debug_gemm2_trace": [vp],
     "vds_loss_fwd_bwd": [vp, vp, vp, vp, vp, vp, i32, i64, f32, vp, vp],
     "vds_adamw": [vp, vp, vp, vp, vp, vp, vp, vp, i32, fp, fp, i32, f32, f32, f32, i32, f32, vp, vp],
