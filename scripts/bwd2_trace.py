@@ -27,15 +27,16 @@ for c in (0, 1):
     for i in list(range(0, 4)) + list(range(40, 46)):
         print(f"{i:4d} " + " ".join(f"{(t[c, i, s].item() - t0) if t[c, i, s].item() else 0:9d}" for s in range(16)))
 d = t[0, 20:100]
-per = (d[-1, 8] - d[0, 8]).item() / (d.shape[0] - 1)
-print("leader mean period (cycles):", per)
 f = lambda a: a.float().mean().item()
-print("issuer: S_wait->rows_ok", f(d[:, 1] - d[:, 0]), " rows_ok->S_issue(stat wait)", f(d[:, 2] - d[:, 1]), " S issue dur", f(d[:, 3] - d[:, 2]),
-      " dp_read wait", f(d[:, 4] - d[:, 3]))
-print("issuer: dP_issue(i+1)->pds_wait(i)", f(d[:-1, 5] - d[1:, 4]), " pds wait", f(d[:, 6] - d[:, 5]), " drained wait", f(d[:, 7] - d[:, 6]),
-      " cols wait", f(d[:, 8] - d[:, 7]), " dQ_issue(i)->S_wait(i+2)", f(d[2:, 0] - d[:-2, 8]))
+per = (d[-1, 6] - d[0, 6]).item() / (d.shape[0] - 1)
+print("leader mean period (cycles):", per)
+print("issuer S(k): rows wait", f(d[:, 1] - d[:, 0]), " stat wait", f(d[:, 2] - d[:, 1]))
+print("issuer dP(k): dp_read wait", f(d[:, 4] - d[:, 3]))
+print("issuer dQ(i-1): dP issue(i+1) -> dq wait start(i-1)", f(d[:-2, 7] - d[2:, 4]), " exchange+drain wait", f(d[:, 8] - d[:, 7]),
+      " dQ issue(i-1) -> pds wait start(i)", f(d[1:, 5] - d[:-1, 8]))
+print("issuer dV/dK(i): pds wait", f(d[:, 6] - d[:, 5]), " pds_ok(i) -> S wait start(i+2)", f(d[2:, 0] - d[:-2, 6]))
 for c in (0, 1):
     e = t[c, 20:100]
     print(f"CTA {c} compute: seesS->exp_done", f(e[:, 10] - e[:, 9]), " wait dP", f(e[:, 11] - e[:, 10]), " dS math", f(e[:, 12] - e[:, 11]),
-          " wait dq_full", f(e[:, 13] - e[:, 12]), " stores+fence+arrive", f(e[:, 14] - e[:, 13]), " pds_arr(i)->seesS(i+1)", f(e[1:, 9] - e[:-1, 14]))
-    print(f"CTA {c}: S_issue(i) [leader] -> seesS(i)", f(e[:, 9] - d[:, 2]), " dQ_issue(i)->drained(i)", f(e[:, 15] - d[:, 8]), " pds_arr(i) -> leader pds_ok(i)", f(d[:, 6] - e[:, 14]))
+          " wait dq_full(i-2)", f(e[:, 13] - e[:, 12]), " stores+fence+arrive+copy", f(e[:, 14] - e[:, 13]), " pds_arr(i)->seesS(i+1)", f(e[1:, 9] - e[:-1, 14]))
+    print(f"CTA {c}: pds_arr(i) -> leader pds_ok(i)", f(d[:, 6] - e[:, 14]), " leader dQ issue(i) -> drained(i)", f(e[:, 15] - d[:, 8]))

@@ -40,10 +40,11 @@ constexpr int B2_COLS_STAGE = 16384;                      // Q cols-half [64 q x
 constexpr int B2_OFF_COLS = B2_OFF_ROWS + 2 * B2_ROWS_STAGE;   // 2 stages                                          32 KiB
 constexpr int B2_OFF_ONES = B2_OFF_COLS + 2 * B2_COLS_STAGE;   // ones tile [128 x 16] no swizzle                    4 KiB
 constexpr int B2_OFF_STAT = B2_OFF_ONES + 4096;           // [buf 0|1][lse | delta] x [32 q x 16] no swizzle          4 KiB
-constexpr int B2_OFF_DS = B2_OFF_STAT + 4096;             // [kv tile 0 | 1] x [128 kv x 32 q] bf16, 64-byte swizzle  16 KiB
-constexpr int B2_OFF_STG = B2_OFF_DS + 16384;             // fp32 [64 q][64 d] staging of the dQ block               16 KiB
-constexpr int B2_OFF_SEND = B2_OFF_STG + 16384;           // this kv tile's dS^T half for the PEER (bulk-copied over DSMEM)  8 KiB
-constexpr int B2_OFF_BAR = B2_OFF_SEND + 8192;
+constexpr int B2_DS_SET = 16384;                          // one set: [kv tile 0 | 1] x [128 kv x 32 q] bf16, 64-byte swizzle
+constexpr int B2_OFF_DS = B2_OFF_STAT + 4096;             // 2 sets (sub-tile parity)                                 32 KiB
+constexpr int B2_OFF_SEND = B2_OFF_DS + 2 * B2_DS_SET;    // 2 sets x this kv tile's dS^T half for the PEER (DSMEM copy) 16 KiB
+constexpr int B2_OFF_STG = B2_OFF_SEND + 2 * 8192;        // fp32 [32 q][64 d] staging of half a dQ block             8 KiB
+constexpr int B2_OFF_BAR = B2_OFF_STG + 8192;
 constexpr int B2_SMEM = B2_OFF_BAR + 256 + 1024;
 
 __device__ __forceinline__ uint32_t mapa_cta(uint32_t cta_addr, uint32_t rank) {
@@ -111,12 +112,24 @@ __device__ __forceinline__ uint64_t desc_mn_sw64(uint32_t addr) {
 // byte offset of 16-byte chunk c (0..3) of row r in a [rows x 64 B] tile with the 64-byte swizzle
 __device__ __forceinline__ uint32_t sw64_offset(uint32_t r, uint32_t c) { return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4); }
 
-// tuning aid: cluster 0 stamps clock64 per sub-tile: dbg[cta][iter][16]
-#define B2_TRACE(slot, it)                                                                              \
-  do {                                                                                                  \
-    if (p.dbg != nullptr && blockIdx.x < 2 && (it) < 160)                                               \
-      p.dbg[((long long)crank * 160 + (it)) * 16 + (slot)] = clock64();                                 \
+// Tuning aid (compile with -DVDS_B2_PROF): cluster 0 accumulates the cycles each role spends in each of its waits and
+// writes them at the end: dbg[cta][role 0 issuer | 1 compute warp 4 | 2 drain warp 8][16] (slot 15 = loop total).
+#ifdef VDS_B2_PROF
+#define B2_PROF_DECL long long prof_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_t0 = clock64();
+#define B2_WAIT(slot, ...) do { const long long t_ = clock64(); __VA_ARGS__; prof_acc[slot] += clock64() - t_; } while (0)
+#define B2_PROF_STORE(role)                                                                                     \
+  do {                                                                                                          \
+    if (p.dbg != nullptr && blockIdx.x < 2 && lane == 0) {                                                      \
+      prof_acc[15] = clock64() - prof_t0;                                                                       \
+      for (int s_ = 0; s_ < 16; ++s_) p.dbg[((long long)crank * 3 + (role)) * 16 + s_] = prof_acc[s_];          \
+    }                                                                                                           \
   } while (0)
+#else
+#define B2_PROF_DECL
+#define B2_WAIT(slot, ...) do { __VA_ARGS__; } while (0)
+#define B2_PROF_STORE(role) do { } while (0)
+#endif
+#define B2_TRACE(slot, it) do { } while (0)
 
 struct AttnBwd2Params {
   AttnBwdParams p;
@@ -142,16 +155,21 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* gSEND = gen + B2_OFF_SEND;
   float* gSTG = reinterpret_cast<float*>(gen + B2_OFF_STG);
   const uint32_t bars = base + B2_OFF_BAR;
-  // barriers that live (are waited on) in the LEADER only: *_full of the TMA rings, and everything the issuer waits for
-  const uint32_t kv_full = bars, rows_full = bars + 8, cols_full = bars + 24, stat_full = bars + 40, dp_read = bars + 56,
-                 pds_full = bars + 64, dq_drained = bars + 72;
+  // Barriers the issuer waits on (the LEADER's copies are used; the follower arrives remotely).  Everything one MMA group
+  // needs is folded into ONE barrier, because each wait costs the single issuing warp ~80-100 cycles even when it has
+  // long completed, and the tensor pipe idles meanwhile (measured: 8 waits = 830 of 2770 cycles per sub-tile):
+  //   s_ready[k & 1]    S^T(k), dP^T(k): rows stage landed (2 producer arrivals + bytes) + statistics tiles written (8 warps)
+  //   dp_read           dP^T(k+1): the compute warps hold dP^T(k) in registers (8 warps)
+  //   dvdk_ready[i & 1] dV(i), dK(i): P^T / dS^T in TMEM (8 warps) + cols stage landed (2 + bytes)
+  //   dq_ready[j & 1]   dQ^T(j): peer's dS^T half landed here (arm + bytes), the follower's relay of the same (1), and
+  //                     dQ^T(j-1) drained out of TMEM (8 warps; pre-arrived by the issuer for j = 0)
+  const uint32_t kv_full = bars, s_ready = bars + 8, dp_read = bars + 24, dvdk_ready = bars + 32, dq_ready = bars + 48;
   // barriers every CTA waits on locally (multicast commits of the leader's MMAs)
   const uint32_t rows_empty = bars + 80, cols_empty = bars + 96, s_full = bars + 112, dp_full = bars + 128,
-                 dq_full = bars + 136, mma_done = bars + 144, tmem_slot = bars + 160;
-  // dS^T exchange: ds_in (every CTA's own) completes when the peer's 8 KiB half has landed in this CTA's sDS;
-  // ds1_ready (leader's) is the follower's relay of its ds_in
-  const uint32_t ds_in = bars + 168, ds1_ready = bars + 176;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + B2_OFF_BAR + 160);
+                 dq_full = bars + 136 /* [2]: by sub-tile parity */, mma_done = bars + 152, tmem_slot = bars + 168;
+  // follower only: the leader's dS^T half has landed in my sDS set (relayed to the leader's dq_ready)
+  const uint32_t ds_in = bars + 176;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + B2_OFF_BAR + 168);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -165,21 +183,18 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 2);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(rows_full + 8 * s, 2);
-      mbar_init(cols_full + 8 * s, 2);
-      mbar_init(stat_full + 8 * s, 8);     // 4 compute warps x 2 CTAs
+      mbar_init(s_ready + 8 * s, 10);
+      mbar_init(dvdk_ready + 8 * s, 10);
+      mbar_init(dq_ready + 8 * s, 10);
       mbar_init(rows_empty + 8 * s, 1);
       mbar_init(cols_empty + 8 * s, 1);
       mbar_init(s_full + 8 * s, 1);
-      mbar_init(mma_done + 8 * s, 1);
+      mbar_init(dq_full + 8 * s, 1);
+      mbar_init(ds_in + 8 * s, 1);
     }
+    mbar_init(mma_done, 1);
     mbar_init(dp_read, 8);
-    mbar_init(pds_full, 8);
-    mbar_init(dq_drained, 8);                // 4 drain warps x 2 CTAs
     mbar_init(dp_full, 1);
-    mbar_init(dq_full, 1);
-    mbar_init(ds_in, 1);
-    mbar_init(ds1_ready, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmQr); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDOr); tma_prefetch_desc(&tmDQ);
@@ -222,8 +237,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int q0 = i * QSUB;
         {
           mbar_wait(rows_empty + 8 * st, us ^ 1u);
-          arm(rows_full + 8 * st, 2 * B2_ROWS_STAGE);
-          const uint32_t fb = lbar(rows_full + 8 * st);
+          arm(s_ready + 8 * st, 2 * B2_ROWS_STAGE);
+          const uint32_t fb = lbar(s_ready + 8 * st);
           const uint32_t dq = sROWS + st * B2_ROWS_STAGE, dd = dq + 8192;
           const int row0 = q0 + (int)crank * 32;
           tma_load_4d_2sm(dq, &tmQr, fb, 0, row0, head, b);
@@ -233,8 +248,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         {
           mbar_wait(cols_empty + 8 * st, us ^ 1u);
-          arm(cols_full + 8 * st, 2 * B2_COLS_STAGE);
-          const uint32_t fb = lbar(cols_full + 8 * st);
+          arm(dvdk_ready + 8 * st, 2 * B2_COLS_STAGE);
+          const uint32_t fb = lbar(dvdk_ready + 8 * st);
           const uint32_t dq = sCOLS + st * B2_COLS_STAGE, dd = dq + 8192;
           tma_load_4d_2sm(dq, &tmQ, fb, (int)crank * 64, q0, head, b);
           tma_load_4d_2sm(dd, &tmDO, fb, (int)crank * 64, q0, head, b);
@@ -244,17 +259,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
+      B2_PROF_DECL
       constexpr uint32_t idesc_s = umma_idesc_bf16(256, 64, false, false);     // S^T, dP^T
       constexpr uint32_t idesc_acc = umma_idesc_bf16(256, 128, false, true);   // dV, dK
       constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 64, true, true);      // dQ^T (64 rows of d per CTA)
       auto issue_s = [&](int k) {
         const int bb = k & 1;
-        if (lane == 0) B2_TRACE(0, k);    // S(k): start waiting
-        mbar_wait(rows_full + 8 * bb, (k >> 1) & 1);
-        if (lane == 0) B2_TRACE(1, k);    // rows landed
-        mbar_wait(stat_full + 8 * bb, (k >> 1) & 1);
+        B2_WAIT(0, mbar_wait(s_ready + 8 * bb, (k >> 1) & 1));
         tc_fence_after();
-        if (lane == 0) B2_TRACE(2, k);    // stats ready: issue
         if (elect_one()) {
           const uint32_t q = sROWS + bb * B2_ROWS_STAGE;
           const uint32_t tST = tSTb + bb * 64;
@@ -266,12 +278,15 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         __syncwarp();
       };
+#ifdef VDS_B2_PROF
+      auto issue_s_t = [&](int k) { const long long t_ = clock64(); issue_s(k); prof_acc[8] += clock64() - t_; };
+#else
+      auto issue_s_t = [&](int k) { issue_s(k); };
+#endif
       auto issue_dp = [&](int k) {
         const int bb = k & 1;
-        if (lane == 0) B2_TRACE(3, k);    // S(k) issued, waiting for dp_read
-        if (k > 0) mbar_wait(dp_read, (k - 1) & 1);
+        if (k > 0) B2_WAIT(2, mbar_wait(dp_read, (k - 1) & 1));
         tc_fence_after();
-        if (lane == 0) B2_TRACE(4, k);    // dP(k) issue
         if (elect_one()) {
           const uint32_t d_o = sROWS + bb * B2_ROWS_STAGE + 8192;
 #pragma unroll
@@ -284,35 +299,19 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         __syncwarp();
       };
-      mbar_wait(kv_full, 0);
-      issue_s(0);
-      issue_dp(0);
-      for (int i = 0; i < n_q; ++i) {
+#ifdef VDS_B2_PROF
+      auto issue_dp_t = [&](int k) { const long long t_ = clock64(); issue_dp(k); prof_acc[9] += clock64() - t_; };
+#else
+      auto issue_dp_t = [&](int k) { issue_dp(k); };
+#endif
+      // dV(i) / dK(i): need P^T / dS^T of both CTAs in TMEM and the cols stage (dvdk_ready)
+      auto issue_dvdk = [&](int i) {
         const int bb = i & 1;
-        if (i + 1 < n_q) {
-          issue_s(i + 1);
-          issue_dp(i + 1);
-        }
-        if (lane == 0) B2_TRACE(5, i);    // waiting for pds_full(i)
-        if (elect_one()) mbar_expect_tx(ds_in, 8192);   // the follower's dS^T half of sub-tile i lands in my sDS slot 1
-        __syncwarp();
-        mbar_wait(pds_full, i & 1);
-        mbar_wait(ds_in, i & 1);
-        mbar_wait(ds1_ready, i & 1);
-        if (lane == 0) B2_TRACE(6, i);
-        if (i > 0) mbar_wait(dq_drained, (i - 1) & 1);
-        if (lane == 0) B2_TRACE(7, i);
-        mbar_wait(cols_full + 8 * bb, (i >> 1) & 1);
+        B2_WAIT(3, mbar_wait(dvdk_ready + 8 * bb, (i >> 1) & 1));
         tc_fence_after();
-        if (lane == 0) B2_TRACE(8, i);    // dQ/dV/dK(i) issue
         if (elect_one()) {
           const uint32_t q = sCOLS + bb * B2_COLS_STAGE, d_o = q + 8192;
           const uint32_t tPT = tSTb + bb * 64;
-#pragma unroll
-          for (int kk = 0; kk < 16; ++kk)   // dQ^T over the 256 kv rows of the pair: tile kk >> 3, 16 rows per k-step
-            mma2_ss(tDQT, umma_smem_desc(sKT + (kk >> 3) * HALF_BYTES + (kk & 7) * 2048, 4096, 1024),
-                    desc_mn_sw64(sDS + (kk >> 3) * 8192 + (kk & 7) * 1024), idesc_dq, kk > 0);
-          commit2(dq_full);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)   // dV += P^T dO : B = this CTA's 64 d columns of dO, MN-major
             mma2_ts(tDV, tPT + kk * 8, umma_smem_desc(d_o + kk * 2048, 8192, 1024), idesc_acc, (i > 0 || kk > 0));
@@ -320,18 +319,61 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int kk = 0; kk < 4; ++kk)   // dK += dS^T Q
             mma2_ts(tDK, tPT + 32 + kk * 8, umma_smem_desc(q + kk * 2048, 8192, 1024), idesc_acc, (i > 0 || kk > 0));
           commit2(cols_empty + 8 * bb);
-          commit2(mma_done + 8 * bb);
+          if (i == n_q - 1) commit2(mma_done);
         }
         __syncwarp();
+      };
+      // dQ^T(j) over the 256 kv rows of the pair: needs both halves of the dS^T exchange of sub-tile j and the drain of j-1
+      auto issue_dq = [&](int j) {
+        const int set = j & 1;
+        B2_WAIT(5, mbar_wait(dq_ready + 8 * set, (j >> 1) & 1));
+        tc_fence_after();
+        if (elect_one()) {
+          if (j + 2 < n_q) mbar_expect_tx(dq_ready + 8 * set, 8192);   // arm this set's next exchange (sub-tile j+2)
+          const uint32_t ds = sDS + set * B2_DS_SET;
+#pragma unroll
+          for (int kk = 0; kk < 16; ++kk)   // tile kk >> 3, 16 kv rows per k-step
+            mma2_ss(tDQT, umma_smem_desc(sKT + (kk >> 3) * HALF_BYTES + (kk & 7) * 2048, 4096, 1024),
+                    desc_mn_sw64(ds + (kk >> 3) * 8192 + (kk & 7) * 1024), idesc_dq, kk > 0);
+          commit2(dq_full + 8 * set);
+        }
+        __syncwarp();
+      };
+      // Program order == tensor-pipe order.  Per sub-tile i:  dP(i+1) | dQ(i-1) | dV(i) dK(i) | S(i+2): dV / dK only need
+      // what the compute warps arrive with (TMEM), so they and the next S^T are not held up by the DSMEM exchange of
+      // dS^T, whose dQ^T runs one sub-tile late out of double-buffered shared-memory tiles.
+      if (elect_one()) {                               // exchanges of sub-tiles 0 and 1
+        mbar_expect_tx(dq_ready, 8192);
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], 8;" ::"r"(dq_ready) : "memory");   // no dQ^T(-1) to drain
+        if (n_q > 1) mbar_expect_tx(dq_ready + 8, 8192);
       }
+      __syncwarp();
+      mbar_wait(kv_full, 0);
+      issue_s(0);
+      issue_dp(0);
+      if (n_q > 1) issue_s(1);
+      for (int i = 0; i < n_q; ++i) {
+        if (i + 1 < n_q) issue_dp_t(i + 1);   // waits for dp_read(i): the middle of compute(i)
+#ifdef VDS_B2_PROF
+        { const long long t_ = clock64(); if (i > 0) issue_dq(i - 1); prof_acc[10] += clock64() - t_; }
+        { const long long t_ = clock64(); issue_dvdk(i); prof_acc[11] += clock64() - t_; }
+#else
+        if (i > 0) issue_dq(i - 1);          // its exchange completes around the same time
+        issue_dvdk(i);                       // end of compute(i)
+#endif
+        if (i + 2 < n_q) issue_s_t(i + 2);
+      }
+      issue_dq(n_q - 1);
+      B2_PROF_STORE(0);
     } else {
       // follower: relay "the leader's dS^T half has landed in my sDS slot 0" to the leader's issuer
-      const uint32_t l_ds1_ready = mapa_cta(ds1_ready, 0);
+      const uint32_t l_dq_ready = mapa_cta(dq_ready, 0);
       for (int i = 0; i < n_q; ++i) {
         if (lane == 0) {
-          mbar_expect_tx(ds_in, 8192);
-          mbar_wait(ds_in, i & 1);
-          mbar_arrive_remote(l_ds1_ready);
+          const uint32_t set = i & 1;
+          mbar_expect_tx(ds_in + 8 * set, 8192);
+          mbar_wait(ds_in + 8 * set, (i >> 1) & 1);
+          mbar_arrive_remote(l_dq_ready + 8 * set);
         }
         __syncwarp();
       }
@@ -350,8 +392,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int which = (ct >> 5) & 1, srow = ct & 31;
     const float* stat_src = (which == 0 ? p.lse : p.delta) + stat_base;
     const float inv_sl2 = 1.0f / p.scale_log2;
-    const uint32_t l_stat_full = mapa_cta(stat_full, 0), l_dp_read = mapa_cta(dp_read, 0), l_pds_full = mapa_cta(pds_full, 0);
-    const uint32_t peer_ds = mapa_cta(sDS, crank ^ 1u), peer_ds_in = mapa_cta(ds_in, crank ^ 1u);
+    const uint32_t l_s_ready = mapa_cta(s_ready, 0), l_dp_read = mapa_cta(dp_read, 0), l_dvdk_ready = mapa_cta(dvdk_ready, 0);
+    // bytes I send complete on the peer's barrier: the leader's dq_ready (sent by the follower) / the follower's ds_in
+    const uint32_t peer_ds = mapa_cta(sDS, crank ^ 1u), peer_ds_in0 = mapa_cta(leader ? ds_in : dq_ready, crank ^ 1u);
     auto stat_fetch = [&](int k) -> float {
       float raw = 0.f;
       if (stat_thread) {
@@ -381,35 +424,50 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       *reinterpret_cast<uint4*>(gONES + k16_off(ct)) = make_uint4(pack_bf16x2(one, one), pack_bf16x2(one, 0.f), 0u, 0u);
       *reinterpret_cast<uint4*>(gONES + k16_off(ct) + 128) = make_uint4(0u, 0u, 0u, 0u);
     }
+    B2_PROF_DECL
     for (int k = 0; k < 2 && k < n_q; ++k) {
       stat_write(k, stat_finish(k, stat_fetch(k)));
       fence_proxy_async_smem();
-      arrive_leader(l_stat_full + 8 * (k & 1));
+      arrive_leader(l_s_ready + 8 * (k & 1));
     }
     for (int i = 0; i < n_q; ++i) {
       const int bb = i & 1;
       const float next_raw = (i + 2 < n_q) ? stat_fetch(i + 2) : 0.f;
-      mbar_wait(s_full + 8 * bb, (i >> 1) & 1);
+      B2_WAIT(0, mbar_wait(s_full + 8 * bb, (i >> 1) & 1));
       tc_fence_after();
-      if (ct == 0) B2_TRACE(9, i);      // compute sees S(i)
       const uint32_t tST = tSTb + bb * 64 + lane_off, tDPT = tDPTs + lane_off;
       // phase 1 (overlaps the dQ/dV/dK MMAs of the previous sub-tile): p = exp2(s'), P^T -> TMEM
+#ifdef VDS_B2_PROF
+      const long long tp1 = clock64();
+#endif
       float pf[64];
       {
         uint32_t sv0[32], sv1[32];
+#ifdef VDS_B2_PROF
+        const long long tl0 = clock64();
+#endif
         tmem_ld32(tST, sv0);
         tmem_ld32(tST + 32, sv1);
         tmem_ld_wait();
+#ifdef VDS_B2_PROF
+        prof_acc[10] += clock64() - tl0;
+#endif
+        const float2 sl2 = make_float2(p.scale_log2, p.scale_log2);
+        // half of the exponentials on the MUFU pipe (ex2.approx), half as a polynomial on the FMA / ALU pipes: the 8192
+        // exp2 per sub-tile are 512 MUFU cycles per SM sub-partition otherwise, a third of the whole sub-tile budget
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float p0 = ex2(__uint_as_float(sv0[e]) * p.scale_log2);
-          float p1 = ex2(__uint_as_float(sv1[e]) * p.scale_log2);
-          if (!kv_full_tile) {
-            p0 = kv_ok ? p0 : 0.f;
-            p1 = kv_ok ? p1 : 0.f;
-          }
-          pf[e] = p0;
-          pf[32 + e] = p1;
+        for (int e = 0; e < 32; e += 4) {
+          const float2 a0 = mul2(make_float2(__uint_as_float(sv0[e]), __uint_as_float(sv0[e + 1])), sl2);
+          const float2 a1 = mul2(make_float2(__uint_as_float(sv0[e + 2]), __uint_as_float(sv0[e + 3])), sl2);
+          const float2 b0 = mul2(make_float2(__uint_as_float(sv1[e]), __uint_as_float(sv1[e + 1])), sl2);
+          const float2 b1 = mul2(make_float2(__uint_as_float(sv1[e + 2]), __uint_as_float(sv1[e + 3])), sl2);
+          const float2 pa1 = ex2_poly2(a1), pb1 = ex2_poly2(b1);
+          pf[e] = ex2(a0.x); pf[e + 1] = ex2(a0.y); pf[e + 2] = pa1.x; pf[e + 3] = pa1.y;
+          pf[32 + e] = ex2(b0.x); pf[32 + e + 1] = ex2(b0.y); pf[32 + e + 2] = pb1.x; pf[32 + e + 3] = pb1.y;
+        }
+        if (!kv_full_tile && !kv_ok) {
+#pragma unroll
+          for (int e = 0; e < 64; ++e) pf[e] = 0.f;
         }
       }
       {
@@ -419,83 +477,117 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_st32(tST, pk);
       }
       // phase 2: dS^T = P^T o dP'^T * scale once dP^T(i) has landed
-      if (ct == 0) B2_TRACE(10, i);     // exp done, waiting for dP(i)
-      mbar_wait(dp_full, i & 1);
+#ifdef VDS_B2_PROF
+      prof_acc[4] += clock64() - tp1;
+#endif
+      B2_WAIT(1, mbar_wait(dp_full, i & 1));
       tc_fence_after();
-      if (ct == 0) B2_TRACE(11, i);
       uint32_t dd[32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t dv[32];
+#ifdef VDS_B2_PROF
+        const long long tl1 = clock64();
+#endif
         tmem_ld32(tDPT + c * 32, dv);
         tmem_ld_wait();
+#ifdef VDS_B2_PROF
+        prof_acc[11] += clock64() - tl1;
+#endif
         if (c == 1) {   // dP^T(i) is in registers: the issuer may refill the buffer with dP^T(i+1)
           tc_fence_before();
           arrive_leader(l_dp_read);
         }
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float d0 = pf[c * 32 + e] * (__uint_as_float(dv[e]) * p.scale);
-          const float d1 = pf[c * 32 + e + 1] * (__uint_as_float(dv[e + 1]) * p.scale);
-          dd[c * 16 + (e >> 1)] = pack_bf16x2(d0, d1);
+        for (int e = 0; e < 32; e += 2) {   // dS^T WITHOUT the softmax scale: the dQ drain and the dK epilogue apply it
+          const float2 d = mul2(make_float2(pf[c * 32 + e], pf[c * 32 + e + 1]),
+                                make_float2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])));
+          dd[c * 16 + (e >> 1)] = pack_bf16x2(d.x, d.y);
         }
       }
       tmem_st32(tST + 32, dd);
-      if (ct == 0) B2_TRACE(12, i);     // math done
-      if (i > 0) mbar_wait(dq_full, (i - 1) & 1);   // dS^T tiles of BOTH CTAs consumed by dQ^T(i-1)
-      if (ct == 0) B2_TRACE(13, i);
+#ifdef VDS_B2_PROF
+      const long long tp3 = clock64();
+#endif
+      const uint32_t set = i & 1;
+      if (i >= 2) B2_WAIT(2, mbar_wait(dq_full + 8 * set, ((i - 2) >> 1) & 1));   // dQ^T(i-2) has consumed this set (and its copies)
       // dS^T row of this kv row: query columns 0..31 belong to CTA 0's B tile, 32..63 to CTA 1's; slot = my kv tile.
-      // My half goes straight into my sDS, the peer's half into the send buffer (same 64-byte-swizzle image), which one
-      // bulk DSMEM copy moves into the peer's sDS (async proxy on both ends: no remote generic stores, no cluster fence).
+      // My half goes straight into my sDS, the peer's half into the send buffer (same 64-byte-swizzle image), which a
+      // bulk DSMEM copy per warp moves into the peer's sDS (async proxy on both ends: no remote generic stores).
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const uint32_t off = sw64_offset(r, c);
         const uint4 h0 = make_uint4(dd[c * 4], dd[c * 4 + 1], dd[c * 4 + 2], dd[c * 4 + 3]);                  // q 0..31
         const uint4 h1 = make_uint4(dd[16 + c * 4], dd[16 + c * 4 + 1], dd[16 + c * 4 + 2], dd[16 + c * 4 + 3]);   // q 32..63
-        *reinterpret_cast<uint4*>(gDS + crank * 8192u + off) = leader ? h0 : h1;
-        *reinterpret_cast<uint4*>(gSEND + off) = leader ? h1 : h0;
+        *reinterpret_cast<uint4*>(gDS + set * B2_DS_SET + crank * 8192u + off) = leader ? h0 : h1;
+        *reinterpret_cast<uint4*>(gSEND + set * 8192u + off) = leader ? h1 : h0;
       }
       // statistics tile of sub-tile i+2 (buffer bb: S^T(i) and dP^T(i), its readers, are complete) shares the fence
       if (i + 2 < n_q) stat_write(i + 2, stat_finish(i + 2, next_raw));
+#ifdef VDS_B2_PROF
+      const long long tp4 = clock64();
+      prof_acc[7] += tp4 - tp3;
+#endif
       tmem_st_wait();
+#ifdef VDS_B2_PROF
+      const long long tp5 = clock64();
+      prof_acc[8] += tp5 - tp4;
+#endif
       fence_proxy_async_smem();
       tc_fence_before();
-      named_bar_sync(3, 128);            // every row of the send buffer is written and fenced
-      if (ct == 0) dsmem_bulk_copy(peer_ds + crank * 8192u, sSEND, 8192, peer_ds_in);
-      arrive_leader(l_pds_full);
-      if (i + 2 < n_q) arrive_leader(l_stat_full + 8 * bb);
-      if (ct == 0) B2_TRACE(14, i);     // pds arrive
+#ifdef VDS_B2_PROF
+      prof_acc[9] += clock64() - tp5;
+#endif
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_remote(l_dvdk_ready + 8 * bb);             // P^T / dS^T in TMEM: dV(i), dK(i) may go
+        const uint32_t wo = set * 8192u + quad * 2048u;       // this warp's 32 rows (2 KiB) of the send buffer
+        dsmem_bulk_copy(peer_ds + set * B2_DS_SET + crank * 8192u + quad * 2048u, sSEND + wo, 2048, peer_ds_in0 + 8 * set);
+        if (i + 2 < n_q) mbar_arrive_remote(l_s_ready + 8 * bb);
+      }
+      __syncwarp();
+#ifdef VDS_B2_PROF
+      prof_acc[6] += clock64() - tp3;
+#endif
     }
+    if (warp == 4) B2_PROF_STORE(1);
   } else if (warp >= 8) {
     // ------------------------------------------------------------------ dQ drain warpgroup
+    B2_PROF_DECL
     const int quad = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const int d_local = (quad & 1) * 32 + lane;   // TMEM lane % 64
     const int qh = quad >> 1;                      // TMEM lane / 64: query columns qh*32 ..
     const bool lead_thread = threadIdx.x == 256;
-    const uint32_t l_dq_drained = mapa_cta(dq_drained, 0);
+    const uint32_t l_dq_ready = mapa_cta(dq_ready, 0);
     for (int i = 0; i < n_q; ++i) {
-      mbar_wait(dq_full, i & 1);
+      B2_WAIT(0, mbar_wait(dq_full + 8 * (i & 1), (i >> 1) & 1));
       tc_fence_after();
       uint32_t v[32];
       tmem_ld32(tDQT + lane_off, v);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(l_dq_drained);
-      if (lead_thread) B2_TRACE(15, i);  // drain: dQ(i) in registers
-      if (lead_thread) bulk_wait_group_read0();      // previous reduction has finished reading the staging tile
-      named_bar_sync(2, 128);
+      if (lane == 0 && i + 1 < n_q) mbar_arrive_remote(l_dq_ready + 8 * ((i + 1) & 1));   // dQ^T(i+1) may overwrite the columns
+      // the 64 (q) x 64 (d) block leaves in two halves through one 8 KiB staging tile: warps 0,1 hold q 0..31, warps 2,3 q 32..63
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        if (lead_thread) bulk_wait_group_read0();      // previous reduction has finished reading the staging tile
+        named_bar_sync(2, 128);
+        if (qh == pass) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) gSTG[(qh * 32 + c) * 64 + d_local] = __uint_as_float(v[c]);
-      fence_proxy_async_smem();
-      named_bar_sync(2, 128);
-      if (lead_thread) {
-        tma_reduce_add_4d(&tmDQ, sSTG, (int)crank * 64, i * QSUB, head, b);
-        bulk_commit_group();
+          for (int c = 0; c < 32; ++c) gSTG[c * 64 + d_local] = __uint_as_float(v[c]) * p.scale;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (lead_thread) {
+          tma_reduce_add_4d(&tmDQ, sSTG, (int)crank * 64, i * QSUB + pass * 32, head, b);
+          bulk_commit_group();
+        }
       }
     }
     if (lead_thread) bulk_wait_group0();
+    if (warp == 8) B2_PROF_STORE(2);
   }
   if (warp >= 4) {
     // dK (compute warpgroup) / dV (drain warpgroup) of this CTA's own kv rows: TMEM lane == kv row
@@ -503,10 +595,11 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    mbar_wait(mma_done + 8 * ((n_q - 1) & 1), ((n_q - 1) >> 1) & 1);
+    mbar_wait(mma_done, 0);
     tc_fence_after();
     const int krow = kv0 + r;
     const uint32_t t = (which == 0 ? tDK : tDV) + lane_off;
+    const float osc = which == 0 ? p.scale : 1.0f;   // dK was accumulated from the unscaled dS^T
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
@@ -518,10 +611,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
-          u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
-          u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
-          u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+          u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * osc, __uint_as_float(v[g * 8 + 1]) * osc);
+          u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * osc, __uint_as_float(v[g * 8 + 3]) * osc);
+          u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * osc, __uint_as_float(v[g * 8 + 5]) * osc);
+          u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * osc, __uint_as_float(v[g * 8 + 7]) * osc);
           *reinterpret_cast<uint4*>(dst + g * 8) = u;
         }
       }
@@ -545,7 +638,7 @@ int launch_attn_bwd_pairs(const void* q, int64_t ldq, const void* k, int64_t ldk
   if ((r = make_tmap_tokens(&tv, v, ldv, Lk, nh, B))) return r;
   if ((r = make_tmap_tokens(&tdo, d_o, lddo, Lq, nh, B, QSUB))) return r;
   if ((r = make_tmap_tokens(&tdor, d_o, lddo, Lq, nh, B, 32))) return r;
-  if ((r = make_tmap_dq(&tdq, p0.dq_acc, p0.lddq, Lq, nh, B, 64))) return r;
+  if ((r = make_tmap_dq(&tdq, p0.dq_acc, p0.lddq, Lq, nh, B, 64, 32))) return r;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);

@@ -106,10 +106,11 @@ static inline int make_tmap_tokens(CUtensorMap* tm, const void* ptr, long long l
   return encode_tmap_bf16(tm, ptr, 4, dims, strides, box);
 }
 // fp32 [B, L, ld] accumulation buffer, box = one [64 rows x box_d floats] sub-tile of one head, no swizzle
-static inline int make_tmap_dq(CUtensorMap* tm, const float* ptr, long long ld, int L, int nh, int B, int box_d = 128) {
+static inline int make_tmap_dq(CUtensorMap* tm, const float* ptr, long long ld, int L, int nh, int B, int box_d = 128,
+                               int box_rows = QSUB) {
   uint64_t dims[4] = {(uint64_t)HD, (uint64_t)L, (uint64_t)nh, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)ld * 4, (uint64_t)HD * 4, (uint64_t)L * (uint64_t)ld * 4};
-  uint32_t box[4] = {(uint32_t)box_d, (uint32_t)QSUB, 1, 1};
+  uint32_t box[4] = {(uint32_t)box_d, (uint32_t)box_rows, 1, 1};
   return encode_tmap(tm, ptr, 1, 4, dims, strides, box, 0);
 }
 

@@ -305,6 +305,23 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
   return *reinterpret_cast<float2*>(&rd);
 }
+// 2^x for two elements on the FMA / ALU pipes instead of the MUFU pipe (FlashAttention-4 style offload): round-to-nearest
+// split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f (max relative error 7.5e-5 in fp32 Horner form —
+// the consumers round to bf16, 3.9e-3), then n is added into the exponent field.  x is clamped at -126 (result ~1e-38),
+// which also maps -inf (masked rows) to a harmless denormal-range value.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.0f);
+  x.y = fmaxf(x.y, -126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);            // 1.5 * 2^23: the sum's low mantissa bits hold n
+  const float2 xr = add2(x, magic);
+  const float2 nf = add2(xr, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = fma2(nf, make_float2(-1.0f, -1.0f), x);
+  float2 q = fma2(make_float2(0.0551716685295105f, 0.0551716685295105f), f, make_float2(0.2426111251115799f, 0.2426111251115799f));
+  q = fma2(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  q = fma2(q, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  return make_float2(__uint_as_float(__float_as_uint(q.x) + (__float_as_uint(xr.x) << 23)),
+                     __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(xr.y) << 23)));
+}
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
