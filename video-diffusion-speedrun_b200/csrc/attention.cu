@@ -6,13 +6,11 @@
 // 4-D TMA tensor maps {d, l, head, b}; the output is written token-major [B, L, nh*128] so the
 // "b h l d -> b l (h d)" rearrange (model.py:137) disappears.
 //
-// Forward CTA = one 128-row query tile of one (b, head):
-//   warp 0  TMA producer (Q once; K/V double-buffered)       warp 1  tcgen05.mma issuer
-//   warps 2-5 softmax: thread == query row (TMEM lane), online softmax in the log2 domain,
-//             P (bf16) -> 128B-swizzled smem as the A operand of P*V, O accumulates in TMEM.
-// Backward CTA = one 128-row K/V tile of one (b, head) looping over query tiles:
-//   S^T = K Q^T, dP^T = V dO^T (TMEM) -> P^T, dS^T (smem, bf16) -> dV += P^T dO, dK += dS^T Q (TMEM),
-//   dQ tile = dS K (TMEM) reduced into an fp32 buffer with red.global.add.
+// Forward CTA = two 128-row query tiles of one (b, head), ping-pong (see attn_fwd_kernel).
+// Backward, 1-CTA kernel (attn_bwd_kernel, below): one 128-row K/V tile of one (b, head) looping over 64-row query
+// sub-tiles; serves cross-attention, query-range splits and the remainder of the CTA-pair kernel.
+// Backward, CTA-pair kernel (attention_bwd2.cu): two adjacent K/V tiles per 2-CTA cluster (tcgen05 cta_group::2); serves
+// whole waves of a self-attention-sized problem.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -876,8 +874,10 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   const int clusters = sms / 2;
   int pairs_main = 0;
   if (pair_mode != 0 && q_splits == 1 && dk != nullptr && dv != nullptr) {
+    // auto: long query ranges only (>= 64 sub-tiles: the pair kernel's longer prologue / epilogue and the extra launch
+    // for the remainder cost more than the ~12 % it gains per sub-tile on short ones: measured at L = 2064)
     if (pair_mode == 2) pairs_main = total_pairs;
-    else if (n_qsub >= 32) pairs_main = (total_pairs / clusters) * clusters;
+    else if (n_qsub >= 64) pairs_main = (total_pairs / clusters) * clusters;
   }
   if (pairs_main > 0) {
     if ((r = launch_attn_bwd_pairs(q, ldq, k, ldk, v, ldv, d_o, lddo, p, B, nh, Lq, Lk, 0, pairs_main, pairs_per_bh, st)))

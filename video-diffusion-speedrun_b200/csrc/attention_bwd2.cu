@@ -19,9 +19,12 @@
 // image of the M128 accumulator, the 64-byte-swizzle MN-major B tile, remote stores feeding the async proxy) were pinned
 // on the hardware with scripts/umma_probe.py before this kernel was written.
 //
-// Roles per CTA (384 threads): warp 0 TMA producer | warp 1 MMA issuer (leader CTA only) | warps 4-7 compute
-// (thread == kv row) | warps 8-11 dQ drain.  All MMA-completion signals are commits multicast to both CTAs' barriers;
-// everything the issuer waits for arrives on the LEADER's barriers (remote arrives from the follower).
+// Roles per CTA (512 threads): warp 0 TMA producer | warp 1 MMA issuer (leader CTA only; relay in the follower) |
+// warps 4-11 compute: thread == kv row, warps 4-7 take query columns 0..31 of the sub-tile and warps 8-11 columns 32..63,
+// i.e. TWO warps per SM sub-partition — one warp per sub-partition ran the ~640 instructions of a sub-tile at IPC 0.33
+// (every FMA / MUFU / conversion latency exposed), two interleave | warps 12-15 dQ drain.  All MMA-completion signals are
+// commits multicast to both CTAs' barriers; everything the issuer waits for arrives on the LEADER's barriers (remote
+// arrives from the follower).
 #include <cuda.h>
 
 #include "attn_common.cuh"
@@ -30,7 +33,7 @@
 
 namespace vds {
 
-constexpr int B2_THREADS = 384;
+constexpr int B2_THREADS = 512;
 constexpr int B2_OFF_K = 0;                               // own K tile, K-major SW128, two 64-wide d halves      32 KiB
 constexpr int B2_OFF_V = B2_OFF_K + TILE_BYTES;           // own V tile                                             32 KiB
 constexpr int B2_OFF_KT = B2_OFF_V + TILE_BYTES;          // [kv tile 0 | 1] x [128 kv x 64 d of THIS CTA's d half]  32 KiB
@@ -158,9 +161,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   // Barriers the issuer waits on (the LEADER's copies are used; the follower arrives remotely).  Everything one MMA group
   // needs is folded into ONE barrier, because each wait costs the single issuing warp ~80-100 cycles even when it has
   // long completed, and the tensor pipe idles meanwhile (measured: 8 waits = 830 of 2770 cycles per sub-tile):
-  //   s_ready[k & 1]    S^T(k), dP^T(k): rows stage landed (2 producer arrivals + bytes) + statistics tiles written (8 warps)
-  //   dp_read           dP^T(k+1): the compute warps hold dP^T(k) in registers (8 warps)
-  //   dvdk_ready[i & 1] dV(i), dK(i): P^T / dS^T in TMEM (8 warps) + cols stage landed (2 + bytes)
+  //   s_ready[k & 1]    S^T(k), dP^T(k): rows stage landed (2 producer arrivals + bytes) + statistics tiles written (16 warps)
+  //   dp_read           dP^T(k+1): the compute warps hold dP^T(k) in registers (16 warps)
+  //   dvdk_ready[i & 1] dV(i), dK(i): P^T / dS^T in TMEM (16 warps) + cols stage landed (2 + bytes)
   //   dq_ready[j & 1]   dQ^T(j): peer's dS^T half landed here (arm + bytes), the follower's relay of the same (1), and
   //                     dQ^T(j-1) drained out of TMEM (8 warps; pre-arrived by the issuer for j = 0)
   const uint32_t kv_full = bars, s_ready = bars + 8, dp_read = bars + 24, dvdk_ready = bars + 32, dq_ready = bars + 48;
@@ -183,8 +186,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 2);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(s_ready + 8 * s, 10);
-      mbar_init(dvdk_ready + 8 * s, 10);
+      mbar_init(s_ready + 8 * s, 18);      // 2 producers + 8 compute warps x 2 CTAs
+      mbar_init(dvdk_ready + 8 * s, 18);
       mbar_init(dq_ready + 8 * s, 10);
       mbar_init(rows_empty + 8 * s, 1);
       mbar_init(cols_empty + 8 * s, 1);
@@ -193,7 +196,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(ds_in + 8 * s, 1);
     }
     mbar_init(mma_done, 1);
-    mbar_init(dp_read, 8);
+    mbar_init(dp_read, 16);
     mbar_init(dp_full, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmQr); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -210,9 +213,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / multicast commit / 2-SM TMA
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_gen;
-  // TMEM columns (same in both CTAs): dV [0,128) | dK [128,256) | S^T buffers [256,320) [320,384) (afterwards bf16 P^T in
-  // their columns 0..31 and dS^T in 32..63) | dP^T [384,448) | dQ^T [448,480): 128 lanes x 32 columns, lane % 64 = d of
-  // this CTA's half, lane / 64 = which 32 query columns
+  // TMEM columns (same in both CTAs): dV [0,128) | dK [128,256) | S^T buffers [256,320) [320,384) (afterwards, per half of
+  // 32 query columns: bf16 P^T in 16 columns, dS^T in the next 16) | dP^T [384,448) | dQ^T [448,480): 128 lanes x 32
+  // columns, lane % 64 = d of this CTA's half, lane / 64 = which 32 query columns
   const uint32_t tDV = tmem, tDK = tmem + 128, tSTb = tmem + 256, tDPTs = tmem + 384, tDQT = tmem + 448;
 
   if (warp == 0) {
@@ -313,11 +316,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const uint32_t q = sCOLS + bb * B2_COLS_STAGE, d_o = q + 8192;
           const uint32_t tPT = tSTb + bb * 64;
 #pragma unroll
+          // A operands in the retired S^T columns: [P^T q 0..31 | dS^T q 0..31 | P^T q 32..63 | dS^T q 32..63] x 16 columns
           for (int kk = 0; kk < 4; ++kk)   // dV += P^T dO : B = this CTA's 64 d columns of dO, MN-major
-            mma2_ts(tDV, tPT + kk * 8, umma_smem_desc(d_o + kk * 2048, 8192, 1024), idesc_acc, (i > 0 || kk > 0));
+            mma2_ts(tDV, tPT + (kk >> 1) * 32 + (kk & 1) * 8, umma_smem_desc(d_o + kk * 2048, 8192, 1024), idesc_acc,
+                    (i > 0 || kk > 0));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)   // dK += dS^T Q
-            mma2_ts(tDK, tPT + 32 + kk * 8, umma_smem_desc(q + kk * 2048, 8192, 1024), idesc_acc, (i > 0 || kk > 0));
+            mma2_ts(tDK, tPT + (kk >> 1) * 32 + 16 + (kk & 1) * 8, umma_smem_desc(q + kk * 2048, 8192, 1024), idesc_acc,
+                    (i > 0 || kk > 0));
           commit2(cols_empty + 8 * bb);
           if (i == n_q - 1) commit2(mma_done);
         }
@@ -378,22 +384,24 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         __syncwarp();
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ------------------------------------------------------------------ compute warpgroup (thread == kv row)
+  } else if (warp >= 4 && warp < 12) {
+    // ------------------------------------------------------------------ compute warps (thread == kv row x half the q columns)
     const int quad = warp & 3;
-    const int r = quad * 32 + lane;
-    const int ct = threadIdx.x - 128;    // 0..127 == r
+    const int r = quad * 32 + lane;              // kv row of the tile == TMEM lane
+    const uint32_t half = (warp - 4) >> 2;       // 0: query columns 0..31 of the sub-tile, 1: columns 32..63
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const bool kv_ok = (kv0 + r) < p.Lk;
     const bool kv_full_tile = kv0 + 128 <= p.Lk;
     const long long stat_base = ((long long)b * p.nh + head) * p.Lq;
-    // statistics tile of this CTA: its 32 query rows of the sub-tile; threads 0..31 write -lse/scale, 32..63 -delta
-    const bool stat_thread = ct < 64;
-    const int which = (ct >> 5) & 1, srow = ct & 31;
+    // statistics tile of this CTA: its 32 query rows of the sub-tile; warp 4 writes -lse/scale, warp 8 -delta
+    const bool stat_thread = quad == 0;
+    const int which = (int)half, srow = lane;
     const float* stat_src = (which == 0 ? p.lse : p.delta) + stat_base;
     const float inv_sl2 = 1.0f / p.scale_log2;
     const uint32_t l_s_ready = mapa_cta(s_ready, 0), l_dp_read = mapa_cta(dp_read, 0), l_dvdk_ready = mapa_cta(dvdk_ready, 0);
-    // bytes I send complete on the peer's barrier: the leader's dq_ready (sent by the follower) / the follower's ds_in
+    // My 32 query columns are the B-tile half of CTA `half`: mine -> straight into my sDS; the peer's -> send buffer, then one
+    // bulk DSMEM copy per warp.  The bytes I send complete on the peer's barrier: the leader's dq_ready / the follower's ds_in.
+    const bool mine = half == crank;
     const uint32_t peer_ds = mapa_cta(sDS, crank ^ 1u), peer_ds_in0 = mapa_cta(leader ? ds_in : dq_ready, crank ^ 1u);
     auto stat_fetch = [&](int k) -> float {
       float raw = 0.f;
@@ -419,10 +427,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(cluster_bar);
     };
-    {  // constant A operand of the statistics k-step: ones in columns 0..2 of every kv row
+    if (half == 0) {  // constant A operand of the statistics k-step: ones in columns 0..2 of every kv row
       const float one = 1.0f;
-      *reinterpret_cast<uint4*>(gONES + k16_off(ct)) = make_uint4(pack_bf16x2(one, one), pack_bf16x2(one, 0.f), 0u, 0u);
-      *reinterpret_cast<uint4*>(gONES + k16_off(ct) + 128) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(gONES + k16_off(r)) = make_uint4(pack_bf16x2(one, one), pack_bf16x2(one, 0.f), 0u, 0u);
+      *reinterpret_cast<uint4*>(gONES + k16_off(r) + 128) = make_uint4(0u, 0u, 0u, 0u);
     }
     B2_PROF_DECL
     for (int k = 0; k < 2 && k < n_q; ++k) {
@@ -436,113 +444,82 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       B2_WAIT(0, mbar_wait(s_full + 8 * bb, (i >> 1) & 1));
       tc_fence_after();
       const uint32_t tST = tSTb + bb * 64 + lane_off, tDPT = tDPTs + lane_off;
-      // phase 1 (overlaps the dQ/dV/dK MMAs of the previous sub-tile): p = exp2(s'), P^T -> TMEM
+      // phase 1 (overlaps the MMAs of the previous sub-tile): p = exp2(s'), P^T -> TMEM
 #ifdef VDS_B2_PROF
       const long long tp1 = clock64();
 #endif
-      float pf[64];
+      float pf[32];
       {
-        uint32_t sv0[32], sv1[32];
-#ifdef VDS_B2_PROF
-        const long long tl0 = clock64();
-#endif
-        tmem_ld32(tST, sv0);
-        tmem_ld32(tST + 32, sv1);
+        uint32_t sv[32];
+        tmem_ld32(tST + half * 32, sv);
         tmem_ld_wait();
-#ifdef VDS_B2_PROF
-        prof_acc[10] += clock64() - tl0;
-#endif
         const float2 sl2 = make_float2(p.scale_log2, p.scale_log2);
         // half of the exponentials on the MUFU pipe (ex2.approx), half as a polynomial on the FMA / ALU pipes: the 8192
-        // exp2 per sub-tile are 512 MUFU cycles per SM sub-partition otherwise, a third of the whole sub-tile budget
+        // exp2 per sub-tile are 512 MUFU cycles per SM sub-partition otherwise
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
-          const float2 a0 = mul2(make_float2(__uint_as_float(sv0[e]), __uint_as_float(sv0[e + 1])), sl2);
-          const float2 a1 = mul2(make_float2(__uint_as_float(sv0[e + 2]), __uint_as_float(sv0[e + 3])), sl2);
-          const float2 b0 = mul2(make_float2(__uint_as_float(sv1[e]), __uint_as_float(sv1[e + 1])), sl2);
-          const float2 b1 = mul2(make_float2(__uint_as_float(sv1[e + 2]), __uint_as_float(sv1[e + 3])), sl2);
-          const float2 pa1 = ex2_poly2(a1), pb1 = ex2_poly2(b1);
+          const float2 a0 = mul2(make_float2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), sl2);
+          const float2 a1 = mul2(make_float2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), sl2);
+          const float2 pa1 = ex2_poly2(a1);
           pf[e] = ex2(a0.x); pf[e + 1] = ex2(a0.y); pf[e + 2] = pa1.x; pf[e + 3] = pa1.y;
-          pf[32 + e] = ex2(b0.x); pf[32 + e + 1] = ex2(b0.y); pf[32 + e + 2] = pb1.x; pf[32 + e + 3] = pb1.y;
         }
         if (!kv_full_tile && !kv_ok) {
 #pragma unroll
-          for (int e = 0; e < 64; ++e) pf[e] = 0.f;
+          for (int e = 0; e < 32; ++e) pf[e] = 0.f;
         }
       }
       {
-        uint32_t pk[32];
+        uint32_t pk[16];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) pk[e] = pack_bf16x2(pf[2 * e], pf[2 * e + 1]);
-        tmem_st32(tST, pk);
+        for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(pf[2 * e], pf[2 * e + 1]);
+        // bf16 P^T of my 32 query columns (pair (2c, 2c+1) per column) over the FIRST 16 of the 32 S^T columns I have
+        // just read; dS^T goes over the other 16.  A warp never writes columns the other half's warp still has to read.
+        tmem_st16(tST + half * 32, pk);
       }
-      // phase 2: dS^T = P^T o dP'^T * scale once dP^T(i) has landed
+      // phase 2: dS^T = P^T o dP'^T once dP^T(i) has landed
 #ifdef VDS_B2_PROF
       prof_acc[4] += clock64() - tp1;
 #endif
       B2_WAIT(1, mbar_wait(dp_full, i & 1));
       tc_fence_after();
-      uint32_t dd[32];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      uint32_t dd[16];
+      {
         uint32_t dv[32];
-#ifdef VDS_B2_PROF
-        const long long tl1 = clock64();
-#endif
-        tmem_ld32(tDPT + c * 32, dv);
+        tmem_ld32(tDPT + half * 32, dv);
         tmem_ld_wait();
-#ifdef VDS_B2_PROF
-        prof_acc[11] += clock64() - tl1;
-#endif
-        if (c == 1) {   // dP^T(i) is in registers: the issuer may refill the buffer with dP^T(i+1)
-          tc_fence_before();
-          arrive_leader(l_dp_read);
-        }
+        tc_fence_before();      // dP^T(i) is in registers: the issuer may refill the buffer with dP^T(i+1)
+        arrive_leader(l_dp_read);
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {   // dS^T WITHOUT the softmax scale: the dQ drain and the dK epilogue apply it
-          const float2 d = mul2(make_float2(pf[c * 32 + e], pf[c * 32 + e + 1]),
-                                make_float2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])));
-          dd[c * 16 + (e >> 1)] = pack_bf16x2(d.x, d.y);
+          const float2 d = mul2(make_float2(pf[e], pf[e + 1]), make_float2(__uint_as_float(dv[e]), __uint_as_float(dv[e + 1])));
+          dd[e >> 1] = pack_bf16x2(d.x, d.y);
         }
       }
-      tmem_st32(tST + 32, dd);
+      tmem_st16(tST + half * 32 + 16, dd);
 #ifdef VDS_B2_PROF
       const long long tp3 = clock64();
 #endif
       const uint32_t set = i & 1;
       if (i >= 2) B2_WAIT(2, mbar_wait(dq_full + 8 * set, ((i - 2) >> 1) & 1));   // dQ^T(i-2) has consumed this set (and its copies)
-      // dS^T row of this kv row: query columns 0..31 belong to CTA 0's B tile, 32..63 to CTA 1's; slot = my kv tile.
-      // My half goes straight into my sDS, the peer's half into the send buffer (same 64-byte-swizzle image), which a
-      // bulk DSMEM copy per warp moves into the peer's sDS (async proxy on both ends: no remote generic stores).
+      {
+        // dS^T of my 32 query columns: 64 bytes of row r in the 64-byte-swizzle tile image of kv tile `crank`
+        uint8_t* dst = mine ? gDS + set * B2_DS_SET + crank * 8192u : gSEND + set * 8192u;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint32_t off = sw64_offset(r, c);
-        const uint4 h0 = make_uint4(dd[c * 4], dd[c * 4 + 1], dd[c * 4 + 2], dd[c * 4 + 3]);                  // q 0..31
-        const uint4 h1 = make_uint4(dd[16 + c * 4], dd[16 + c * 4 + 1], dd[16 + c * 4 + 2], dd[16 + c * 4 + 3]);   // q 32..63
-        *reinterpret_cast<uint4*>(gDS + set * B2_DS_SET + crank * 8192u + off) = leader ? h0 : h1;
-        *reinterpret_cast<uint4*>(gSEND + set * 8192u + off) = leader ? h1 : h0;
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(dst + sw64_offset(r, c)) = make_uint4(dd[c * 4], dd[c * 4 + 1], dd[c * 4 + 2], dd[c * 4 + 3]);
       }
       // statistics tile of sub-tile i+2 (buffer bb: S^T(i) and dP^T(i), its readers, are complete) shares the fence
       if (i + 2 < n_q) stat_write(i + 2, stat_finish(i + 2, next_raw));
-#ifdef VDS_B2_PROF
-      const long long tp4 = clock64();
-      prof_acc[7] += tp4 - tp3;
-#endif
       tmem_st_wait();
-#ifdef VDS_B2_PROF
-      const long long tp5 = clock64();
-      prof_acc[8] += tp5 - tp4;
-#endif
       fence_proxy_async_smem();
       tc_fence_before();
-#ifdef VDS_B2_PROF
-      prof_acc[9] += clock64() - tp5;
-#endif
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_remote(l_dvdk_ready + 8 * bb);             // P^T / dS^T in TMEM: dV(i), dK(i) may go
-        const uint32_t wo = set * 8192u + quad * 2048u;       // this warp's 32 rows (2 KiB) of the send buffer
-        dsmem_bulk_copy(peer_ds + set * B2_DS_SET + crank * 8192u + quad * 2048u, sSEND + wo, 2048, peer_ds_in0 + 8 * set);
+        if (!mine) {                                           // this warp's 32 rows (2 KiB) of the send buffer
+          const uint32_t wo = set * 8192u + quad * 2048u;
+          dsmem_bulk_copy(peer_ds + set * B2_DS_SET + crank * 8192u + quad * 2048u, sSEND + wo, 2048, peer_ds_in0 + 8 * set);
+        }
         if (i + 2 < n_q) mbar_arrive_remote(l_s_ready + 8 * bb);
       }
       __syncwarp();
@@ -551,14 +528,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #endif
     }
     if (warp == 4) B2_PROF_STORE(1);
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ------------------------------------------------------------------ dQ drain warpgroup
     B2_PROF_DECL
     const int quad = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const int d_local = (quad & 1) * 32 + lane;   // TMEM lane % 64
     const int qh = quad >> 1;                      // TMEM lane / 64: query columns qh*32 ..
-    const bool lead_thread = threadIdx.x == 256;
+    const bool lead_thread = threadIdx.x == 384;
     const uint32_t l_dq_ready = mapa_cta(dq_ready, 0);
     for (int i = 0; i < n_q; ++i) {
       B2_WAIT(0, mbar_wait(dq_full + 8 * (i & 1), (i >> 1) & 1));
@@ -587,10 +564,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
     }
     if (lead_thread) bulk_wait_group0();
-    if (warp == 8) B2_PROF_STORE(2);
+    if (warp == 12) B2_PROF_STORE(2);
   }
-  if (warp >= 4) {
-    // dK (compute warpgroup) / dV (drain warpgroup) of this CTA's own kv rows: TMEM lane == kv row
+  if (warp >= 4 && warp < 12) {
+    // dK (warps 4-7) / dV (warps 8-11) of this CTA's own kv rows: TMEM lane == kv row
     const int which = warp >= 8 ? 1 : 0;
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
