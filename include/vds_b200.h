@@ -129,6 +129,10 @@ int vds_qkv_post_bwd(void* dqkv, const float* dq_acc, const float* cos, const fl
 int vds_colsum(const void* x, float* out, int64_t rows, int n, int64_t ld, void* stream);
 int vds_batch_rowsum(const void* x, float* out, int B, int64_t batch_stride, int rows, int h, void* stream);
 int vds_cast_f32_bf16(const float* x, void* y, int64_t n, float scale, void* stream);
+/* same for a 2-D block with leading dimensions: x fp32 [rows, cols] (ldx) -> y bf16 [rows, cols] (ldy); used to drop a
+ * block's dK / dV of the cross-attention (model.py:149-157 backward) into its column slice of the grouped context_kv gradient */
+int vds_cast_f32_bf16_2d(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int cols, float scale,
+                         void* stream);
 int vds_accum_bf16_f32(const void* x, float* y, int64_t n, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------ attention

@@ -49,7 +49,11 @@ def main():
     latent, noise, context, t = data(rank, dev)
     losses = []
     stepper = train.GraphedTrainStep(model, opt, latent.shape, context.shape, device=dev, warmup=1) if GRAPH else None
+    dbg = os.environ.get("VDS_MGPU_DEBUG") == "1"
     for step in range(NSTEPS):
+        if dbg:
+            torch.cuda.synchronize()
+            print(f"[rank {rank}] step {step} begin", flush=True)
         torch.manual_seed(50 + step)
         if stepper is not None:     # step 0 eager on the capture stream, step 1 captures + replays, steps 2.. replay
             loss = stepper(latent, context, t, noise, caption_dropout=0.0).clone()
@@ -60,6 +64,8 @@ def main():
             opt.step()
         losses.append(loss.detach())
     torch.cuda.synchronize()
+    if dbg:
+        print(f"[rank {rank}] steps done", flush=True)
     if stepper is not None:
         assert stepper.graph is not None, "the multi-GPU step was not captured"
     sd = model.state_dict()  # full tensors (all-gathers the fp32 master shards)

@@ -160,3 +160,46 @@ def test_dgrad_rowdot_epilogue_matches_separate_kernels(cuda_dev):
     # shapes without a 2-CTA tile path report "unsupported" (None) instead of computing something else
     small = ops.gemm_dgrad_rowdot(dy[:256], w, o[:256], torch.zeros((1, nh, 256), device=cuda_dev), 256)
     assert small is None
+
+
+def test_gemm_xl_width_narrow_last_tile(cuda_dev):
+    """DiT-XL width (h = 1152, 9 heads): N = 1152 / 3456 are not multiples of the 256-wide 2-CTA tile; the last tile is
+    computed on TMA zero-fill and clipped.  Every epilogue of the step, at shapes large enough for the 2-CTA path."""
+    from vds_b200 import ops, lib
+    Bt, Lr, h = 4, 2064 * 2, 1152
+    M = Bt * Lr
+    a = _mk((M, h), cuda_dev, 50)
+    # qkv: STORE with bias, N = 3456
+    wq, bq = _mk((3 * h, h), cuda_dev, 51, 0.03), _mk((3 * h,), cuda_dev, 52)
+    _close(ops.gemm(a, wq, bias=bq), a.float() @ wq.float().t() + bq.float())
+    # attn_proj: GATE_RES, N = 1152
+    wp, x, gate = _mk((h, h), cuda_dev, 53, 0.03), _mk((M, h), cuda_dev, 54), _mk((Bt, 9 * h), cuda_dev, 55)
+    g = gate[:, 2 * h:3 * h]
+    lin, xo = ops.gemm(a, wp, epilogue=lib.EPI_GATE_RES, aux=x, gate=g, rows_per_batch=Lr)
+    ref_lin = (a.float() @ wp.float().t()).bfloat16()
+    _close(lin, ref_lin)
+    _close(xo, x + (lin.view(Bt, Lr, h) * g[:, None, :]).view(M, h), tol=1e-2)
+    # dgrad of attn_proj with the attention delta (STORE_ROWDOT), N = 1152 = 9 heads
+    dy, o = _mk((M, h), cuda_dev, 56), _mk((M, h), cuda_dev, 57)
+    rowdot = torch.zeros((Bt, h // 128, Lr), device=cuda_dev, dtype=torch.float32)
+    dx = ops.gemm_dgrad_rowdot(dy, wp, o, rowdot, Lr)
+    assert dx is not None
+    ref_dx = (dy.float() @ wp.float()).bfloat16()
+    _close(dx, ref_dx)
+    ref_dot = (ref_dx.float() * o.float()).view(Bt, Lr, h // 128, 128).sum(-1).permute(0, 2, 1)
+    _close(rowdot, ref_dot, tol=2e-2)
+    # mlp: BIAS_GELU N = 4608 (multiple of 256) then DGELU dgrad back to N = 4608 and the mlp.2 GATE_RES N = 1152
+    w1, b1 = _mk((4 * h, h), cuda_dev, 58, 0.03), _mk((4 * h,), cuda_dev, 59)
+    pre, act = ops.gemm(a, w1, bias=b1, epilogue=lib.EPI_BIAS_GELU)
+    w2, b2 = _mk((h, 4 * h), cuda_dev, 60, 0.02), _mk((h,), cuda_dev, 61)
+    lin2, xo2 = ops.gemm(act, w2, bias=b2, epilogue=lib.EPI_GATE_RES, aux=x, gate=g, rows_per_batch=Lr)
+    ref_lin2 = (act.float() @ w2.float().t() + b2.float()).bfloat16()
+    _close(lin2, ref_lin2)
+    _close(xo2, x + (lin2.view(Bt, Lr, h) * g[:, None, :]).view(M, h), tol=1e-2)
+    # wgrad of qkv: M = 3456, N = 1152, fp32 split-K accumulate
+    dqkv = _mk((M, 3 * h), cuda_dev, 62)
+    gw = torch.zeros((3 * h, h), device=cuda_dev, dtype=torch.float32)
+    ops.gemm(dqkv, a, a_mn=True, b_mn=True, epilogue=lib.EPI_ACCUM_F32, out=gw, splits=4)
+    _close(gw, dqkv.float().t() @ a.float())
+    # dgrad of qkv: [M, 3456] x [3456, 1152] -> N = 1152
+    _close(ops.gemm(dqkv, wq, b_mn=True), dqkv.float() @ wq.float())

@@ -56,6 +56,36 @@ def test_layout_covers_every_parameter_exactly_once(world):
             assert all(h == group_of[n] for h in hits)
 
 
+@pytest.mark.parametrize("world,G", [(1, 3), (2, 2), (8, 1), (3, 2)])
+def test_layout_context_kv_groups_are_contiguous_stacks(world, G):
+    """ckv_group = G: the context_kv Linear of every block moves into groups of G consecutive blocks whose weights
+    (then biases) sit back to back, so G blocks' worth are ONE [G*2h, Dc] GEMM operand; everything else is unchanged."""
+    from vds_b200.shard import Layout
+    m, shapes = _shapes()
+    depth, h, Dc = CFG["depth"], CFG["hidden_size"], CFG["cross_attn_input_size"]
+    lay = Layout(shapes, depth, world, ckv_group=G)
+    n_ckv = (depth + G - 1) // G
+    assert lay.n_ckv == n_ckv and lay.n_groups == depth + 1 + n_ckv
+    seen = set()
+    for i in range(depth):
+        gi, j, nb = lay.ckv_of_block(i)
+        assert gi == i // G and j == i % G and nb == min(G, depth - gi * G)
+        (ws, rows, cols), bias = lay.ckv_ranges(gi)
+        assert rows == nb * 2 * h and cols == Dc
+        s, numel = lay.full_range(f"blocks.{i}.context_kv.weight")
+        assert s == ws + j * 2 * h * Dc and numel == 2 * h * Dc                   # block i = rows [j*2h, (j+1)*2h) of the stack
+        bs, bn = lay.full_range(f"blocks.{i}.context_kv.bias")
+        assert bias is not None and bs == bias[0] + j * 2 * h and bias[1] == nb * 2 * h
+        assert lay.param[f"blocks.{i}.qkv.weight"][0] == i                        # the rest of the block stays in its group
+        seen.add(gi)
+    assert seen == set(range(n_ckv))
+    covered = torch.zeros(lay.full_total, dtype=torch.int32)
+    for name, shape in shapes:
+        s, numel = lay.full_range(name)
+        covered[s:s + numel] += 1
+    assert covered.max().item() == 1 and covered.sum().item() == sum(p.numel() for p in m.parameters())
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -90,6 +120,8 @@ def _worker(rank, world, port, out):
             flat.grad_views[n].copy_(ref[n] * (rank + 1))
         for g in range(flat.depth):
             flat.block_backward_done(g)
+        for gi in range(flat.layout.n_ckv):       # grouped context_kv parameters live in their own groups
+            flat.ckv_backward_done(gi)
         flat.end_backward()
         mean = sum(range(1, world + 1)) / world
         for n, p in m.named_parameters():

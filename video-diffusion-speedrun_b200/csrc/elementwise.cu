@@ -691,6 +691,23 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restri
     for (long long j = i; j < n; ++j) y[j] = __float2bfloat16_rn(x[j] * scale);
   }
 }
+// 2-D variant: x fp32 [rows, cols] (leading dim ldx) -> y bf16 [rows, cols] (leading dim ldy); cols % 4 == 0
+__global__ void cast_f32_bf16_2d_kernel(const float* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                        long long rows, int cols, float scale) {
+  pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
+  pdl_trigger();
+  const int c4 = cols / 4;
+  const long long total = rows * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4;
+    const int c = (int)(i % c4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    uint2 u;
+    u.x = pack_bf16x2(v.x * scale, v.y * scale);
+    u.y = pack_bf16x2(v.z * scale, v.w * scale);
+    *reinterpret_cast<uint2*>(y + r * ldy + c) = u;
+  }
+}
 // y(fp32) (+)= float(x(bf16))
 __global__ void accum_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n, int accumulate) {
   pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
@@ -888,6 +905,17 @@ int vds_batch_rowsum(const void* x, float* out, int B, int64_t batch_stride, int
 int vds_cast_f32_bf16(const float* x, void* y, int64_t n, float scale, void* stream) {
   launch_k(cast_f32_bf16_kernel, ceil_div(ceil_div(n, 4), 256), 256, 0, (cudaStream_t)stream, x, (bf16*)y, n, scale);
   VDS_CHECK_LAUNCH("cast_f32_bf16");
+  return VDS_OK;
+}
+int vds_cast_f32_bf16_2d(const float* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int cols, float scale,
+                         void* stream) {
+  VDS_CHECK_ARG(cols % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 7) == 0,
+                "cast_f32_bf16_2d: cols / leading dims must be multiples of 4 and the pointers 16- / 8-byte aligned");
+  const long long total = rows * (cols / 4);
+  const int grid = min(ceil_div(total, 256), num_sms() * 16);
+  launch_k(cast_f32_bf16_2d_kernel, grid, 256, 0, (cudaStream_t)stream, x, (long long)ldx, (bf16*)y, (long long)ldy,
+           (long long)rows, cols, scale);
+  VDS_CHECK_LAUNCH("cast_f32_bf16_2d");
   return VDS_OK;
 }
 int vds_accum_bf16_f32(const void* x, float* y, int64_t n, int accumulate, void* stream) {

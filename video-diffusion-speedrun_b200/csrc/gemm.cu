@@ -358,11 +358,11 @@ extern "C" int vds_gemm(const vds_gemm_args* args, void* stream) {
   VDS_CHECK_ARG(a.C != nullptr || a.C2 != nullptr, "gemm: no output");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // 2-CTA (cta_group::2) 256 x 256 tiles when they can keep every SM pair busy
-  if (a.cluster != 1 && a.tile_n != 128 && a.N % 256 == 0) {
+  if (a.cluster != 1 && a.tile_n != 128 && a.N % 64 == 0 && a.N >= 256) {
     const int k_iters = (a.K + BK - 1) / BK;
     int splits = (a.epilogue == VDS_EPI_ACCUM_F32) ? (a.splits < 1 ? 1 : a.splits) : 1;
     if (splits > k_iters) splits = k_iters;
-    const long long pair_tiles = (long long)((a.M + 255) / 256) * (a.N / 256) * splits;
+    const long long pair_tiles = (long long)((a.M + 255) / 256) * ((a.N + 255) / 256) * splits;
     if (pair_tiles >= num_sms() / 2) {
       const int r = gemm2_dispatch(a, s);
       if (r != VDS_ERR_UNSUPPORTED) return r;

@@ -147,16 +147,18 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
       float dot = 0.f;  // STORE_ROWDOT: this row's partial <C, aux> over the 64 columns of the group
       const int b = (EPI == VDS_EPI_GATE_RES) ? min(row0 + lane, p.M - 1) / p.rows_per_batch : 0;
       uint4 bnext = make_uint4(0u, 0u, 0u, 0u), gnext = make_uint4(0u, 0u, 0u, 0u);
-      if (has_bias) bnext = __ldg(reinterpret_cast<const uint4*>(p.bias + col0));
+      const bool col_ok = col0 < p.N;        // false: a 64-column group past N (last, narrower tile): math on zeros, stores clipped
+      const bool ld_bias = has_bias && col_ok;
+      if (ld_bias) bnext = __ldg(reinterpret_cast<const uint4*>(p.bias + col0));
       if constexpr (EPI == VDS_EPI_GATE_RES)
-        gnext = __ldg(reinterpret_cast<const uint4*>(p.gate + (long long)b * p.gate_stride + col0));
+        if (col_ok) gnext = __ldg(reinterpret_cast<const uint4*>(p.gate + (long long)b * p.gate_stride + col0));
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const uint4 braw = bnext, graw = gnext;
         if (g < 7) {   // per-column operands one chunk ahead (L1-resident after the first warp touched them)
-          if (has_bias) bnext = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + (g + 1) * 8));
+          if (ld_bias) bnext = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + (g + 1) * 8));
           if constexpr (EPI == VDS_EPI_GATE_RES)
-            gnext = __ldg(reinterpret_cast<const uint4*>(p.gate + (long long)b * p.gate_stride + col0 + (g + 1) * 8));
+            if (col_ok) gnext = __ldg(reinterpret_cast<const uint4*>(p.gate + (long long)b * p.gate_stride + col0 + (g + 1) * 8));
         }
         uint4 outv;
         float a8[8];
@@ -228,7 +230,7 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
       tq = clock64();
       if constexpr (EPI == VDS_EPI_STORE_ROWDOT) {
         const int row = row0 + lane;
-        if (row < p.M) {
+        if (row < p.M && col_ok) {
           const int bb = row / p.rows_per_batch, rr = row % p.rows_per_batch;
           float* dst = reinterpret_cast<float*>(p.C2) + ((long long)bb * (p.N >> 7) + (col0 >> 7)) * p.rows_per_batch + rr;
           atomicAdd(dst, dot);   // two 64-column groups per head: a two-term sum, order-independent
@@ -314,7 +316,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot_gen;
 
   const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
-  const int n_tiles = p.N / G2_BN;
+  const int n_tiles = (p.N + G2_BN - 1) / G2_BN;   // N % 64 == 0; the columns past N of the last tile are TMA zero-fill / clipped
   const int k_iters = (p.K + BK - 1) / BK;
   const int total_tiles = m_pairs * n_tiles * p.splits;
   const int tile0 = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
@@ -571,7 +573,7 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
     }
     attr_set = true;
   }
-  const long long total = (long long)((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / G2_BN) * p.splits;
+  const long long total = (long long)((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + G2_BN - 1) / G2_BN) * p.splits;
   const int max_pairs = num_sms() / 2;
   const int grid = (int)(total < max_pairs ? total : max_pairs) * 2;
   cudaLaunchConfig_t cfg = {};
@@ -601,7 +603,9 @@ void gemm2_set_trace(long long* p) { g_gemm2_trace = p; }
 
 // Entry used by gemm.cu's dispatcher: returns VDS_ERR_UNSUPPORTED when the shape / epilogue has no 2-CTA variant.
 int gemm2_dispatch(const vds_gemm_args& a, cudaStream_t s) {
-  if (a.N % G2_BN != 0) return VDS_ERR_UNSUPPORTED;
+  // N needs whole 64-column groups (every epilogue works on those); a last tile narrower than 256 (N = 1152, 3456 of the
+  // DiT-XL width) is computed full width on zero-filled B rows and clipped on the way out
+  if (a.N % 64 != 0 || a.N < G2_BN) return VDS_ERR_UNSUPPORTED;
   if (!a.a_mn && !a.b_mn) {
     switch (a.epilogue) {
       case VDS_EPI_STORE: return launch_gemm2<false, false, VDS_EPI_STORE>(a, s);

@@ -117,9 +117,21 @@ def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise
 
     blocks = []
     v0 = None
+    # Training with flat (sharded) parameters: context_kv(context) of G consecutive blocks is ONE GEMM on the stacked
+    # [G*2h, Dc] weight (shard.Layout: ckv groups) — every block applies its own Linear to the SAME caption embedding
+    # (model.py:149-155), so the grouping is result-identical and turns depth small-N GEMMs into a few chip-filling ones.
+    lay = P.flat.layout if (P.flat is not None and has_cross) else None
+    grouped_ckv = lay is not None and lay.ckv_group > 0 and getattr(model, "_ckv_cache", None) is None
+    ckv_g = None
     for i in range(depth):
         pre = f"blocks.{i}."
         s = Ctx()
+        if grouped_ckv:
+            gi, gj, gnb = lay.ckv_of_block(i)
+            if gj == 0:
+                P.wait_group(depth + 1 + gi)
+                Wg, bg, _, _ = P.flat.ckv_views(gi)
+                ckv_g = ops.gemm(ctx2d, Wg, bias=bg)        # [B*Lc, nb*2h]
         P.wait_group(i)
         mod = ops.gemm(sc, P[pre + "adaLN_modulation.1.weight"], bias=P[pre + "adaLN_modulation.1.bias"])
         shift_sa, scale_sa, gate_sa, shift_ca, scale_ca, gate_ca, shift_mlp, scale_mlp, gate_mlp = _chunks(mod, h)
@@ -151,6 +163,8 @@ def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise
                 ent = cache.get((i, id(context)))   # the entry holds `context`, so its id cannot be recycled
                 if ent is not None and ent[0] is context and ent[1] == context._version:
                     ckv = ent[2]
+            if ckv is None and grouped_ckv:
+                ckv = ckv_g[:, gj * 2 * h:(gj + 1) * 2 * h]      # this block's columns of the grouped output
             if ckv is None:
                 ckv = ops.gemm(ctx2d, P[pre + "context_kv.weight"], bias=P.get(pre + "context_kv.bias"))
                 if cache is not None:
@@ -189,6 +203,7 @@ def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise
     c.ctx2d = ctx2d if has_cross else None
     c.Lc = Lc if has_cross else 0
     c.has_cross, c.residual_v = has_cross, residual_v
+    c.grouped_ckv = grouped_ckv
     return out, c
 
 
@@ -201,6 +216,7 @@ class GradSink:
         self.dev = dev
         self._shapes = getattr(model, "_full_shapes", None) or {n: p.shape for n, p in model.named_parameters()}
         self.on_block_done = None
+        self.on_ckv_done = None
 
     def buf(self, name):
         t = self.g.get(name)
@@ -297,6 +313,8 @@ def backward(model, P, c, dout, sink):
         if qs > 1:
             sizes["dckv_f"] = B * c.Lc * 2 * h
     arena = ZeroArena(dev, sizes)
+    lay = P.flat.layout if (P.flat is not None and c.has_cross) else None
+    dckv_g = None
     for i in reversed(range(depth)):
         pre = f"blocks.{i}."
         s = c.blocks[i]
@@ -325,18 +343,36 @@ def backward(model, P, c, dout, sink):
             if dca is None:
                 dca, delta2 = ops.gemm(do2, P[pre + "cross_proj.weight"], b_mn=True), None
             dq_acc = arena.get("dq_cross", (B * Lr, h))
+            if c.grouped_ckv:   # this block's column slice of the group's [B*Lc, nb*2h] gradient (one wgrad per group)
+                gi, gj, gnb = lay.ckv_of_block(i)
+                if dckv_g is None:
+                    dckv_g = torch.empty((B * Lc, gnb * 2 * h), device=dev, dtype=torch.bfloat16)
+                dckv = dckv_g[:, gj * 2 * h:(gj + 1) * 2 * h]
+            else:
+                dckv = torch.empty((B * Lc, 2 * h), device=dev, dtype=torch.bfloat16)
             if qs > 1:
                 dckv_f = arena.get("dckv_f", (B * Lc, 2 * h))
                 ops.attn_bwd(s.qc, s.ckv[:, :h], s.ckv[:, h:], s.ca, dca, s.lse2, B, nh, Lr, Lc, dq_acc,
                              dk_acc=dckv_f[:, :h], dv_acc=dckv_f[:, h:], q_splits=qs, delta=delta2)
-                dckv = ops.cast_f32_bf16(dckv_f)
+                ops.cast_f32_bf16_2d(dckv_f, dckv)
             else:
-                dckv = torch.empty((B * Lc, 2 * h), device=dev, dtype=torch.bfloat16)
                 ops.attn_bwd(s.qc, s.ckv[:, :h], s.ckv[:, h:], s.ca, dca, s.lse2, B, nh, Lr, Lc, dq_acc,
                              dk=dckv[:, :h], dv=dckv[:, h:], delta=delta2)
             dqc = ops.cast_f32_bf16(dq_acc)
-            sink.wgrad(pre + "context_kv.weight", dckv, c.ctx2d)
-            sink.bgrad(pre + "context_kv.bias", dckv)
+            if c.grouped_ckv:
+                if gj == 0:     # first block of the group = last one in backward order: the group's gradient is complete
+                    _, _, gWg, gbg = P.flat.ckv_views(gi)
+                    Kc = B * Lc
+                    ops.gemm(dckv_g, c.ctx2d, a_mn=True, b_mn=True, epilogue=L.EPI_ACCUM_F32, out=gWg,
+                             splits=max(1, min(16, Kc // 2048)), K=Kc)
+                    if gbg is not None:
+                        ops.colsum(dckv_g, gbg)
+                    dckv_g = None
+                    if sink.on_ckv_done is not None:
+                        sink.on_ckv_done(gi)
+            else:
+                sink.wgrad(pre + "context_kv.weight", dckv, c.ctx2d)
+                sink.bgrad(pre + "context_kv.bias", dckv)
             sink.wgrad(pre + "q_cross.weight", dqc, s.n2)
             sink.bgrad(pre + "q_cross.bias", dqc)
             dn2 = ops.gemm(dqc, P[pre + "q_cross.weight"], b_mn=True)
@@ -412,6 +448,7 @@ def run_backward(model, P, c, dout, dtypes):
         flat.begin_backward()
         sink = GradSink(model, dout.device, flat.grad_views)
         sink.on_block_done = flat.block_backward_done
+        sink.on_ckv_done = flat.ckv_backward_done
         with ops.pinned_stream():
             backward(model, P, c, dout, sink)
         flat.end_backward()

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "vds_colsum": [vp, vp, i64, i32, i64, vp],
     "vds_batch_rowsum": [vp, vp, i32, i64, i32, i32, vp],
     "vds_cast_f32_bf16": [vp, vp, i64, f32, vp],
+    "vds_cast_f32_bf16_2d": [vp, i64, vp, i64, i64, i32, f32, vp],
     "vds_accum_bf16_f32": [vp, vp, i64, i32, vp],
     "vds_attn_fwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i32, i32, i32, i32, i32, f32, vp],
     "vds_attn_bwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp, i64, vp, vp,

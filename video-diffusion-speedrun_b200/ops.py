@@ -248,6 +248,15 @@ def cast_f32_bf16(x, out=None, scale=1.0):
     return out
 
 
+def cast_f32_bf16_2d(x, out, scale=1.0):
+    """x fp32 [rows, cols] -> out bf16 [rows, cols]; both may be column slices of wider buffers (unit inner stride)."""
+    assert x.dtype == torch.float32 and out.dtype == torch.bfloat16 and x.shape == out.shape and x.dim() == 2
+    assert x.stride(1) == 1 and out.stride(1) == 1
+    L.check(L.lib().vds_cast_f32_bf16_2d(_p(x), x.stride(0), _p(out), out.stride(0), x.shape[0], x.shape[1], scale, _s()),
+            "vds_cast_f32_bf16_2d")
+    return out
+
+
 def accum_bf16_f32(x, out, accumulate=True):
     _chk_bf16(x)
     assert out.dtype == torch.float32 and x.is_contiguous() and out.is_contiguous()

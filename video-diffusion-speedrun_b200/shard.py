@@ -15,6 +15,8 @@ reshard/re-gather, half the all-gather traffic; 180 GB of HBM makes this free). 
 side stream right after the optimizer step, block 0 first, and the forward waits per group; the
 reduce-scatter of block i runs on the side stream while block i-1 is still in backward.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -28,16 +30,33 @@ def _round_up(x, m):
 
 
 class Layout:
-    """Pure-python layout math (device-free; unit-tested on CPU)."""
+    """Pure-python layout math (device-free; unit-tested on CPU).
 
-    def __init__(self, named_shapes, depth, world):
+    Groups = one per DiTBlock + one root group (the reference's FSDP grouping, model.py:523-541).  With ``ckv_group = G``
+    > 0 the ``context_kv`` Linear of every block is moved out of its block into extra groups of G consecutive blocks,
+    laid out back to back ([weights of the G blocks][biases]): the K = 4096 GEMM of ``model.py:149-155`` has the same A
+    operand (the caption embedding) in every block, so G blocks' worth run as ONE ``[B*Lc, 4096] x [4096, G*2h]`` GEMM
+    (and one wgrad) on a contiguous ``[G*2h, 4096]`` weight.  Results are identical."""
+
+    def __init__(self, named_shapes, depth, world, ckv_group=0):
         self.world = world
-        groups = [[] for _ in range(depth + 1)]  # depth blocks + root (last)
+        self.depth = depth
+        self.ckv_group = int(ckv_group) if ckv_group and ckv_group > 0 else 0
+        self.n_ckv = (depth + self.ckv_group - 1) // self.ckv_group if self.ckv_group else 0
+        groups = [[] for _ in range(depth + 1 + self.n_ckv)]  # depth blocks + root + ckv groups
+        ckv_w = [[] for _ in range(self.n_ckv)]
+        ckv_b = [[] for _ in range(self.n_ckv)]
         for n, shape in named_shapes:
             if n.startswith("blocks."):
-                groups[int(n.split(".")[1])].append((n, tuple(shape)))
+                bi = int(n.split(".")[1])
+                if self.ckv_group and ".context_kv." in n:
+                    (ckv_w if n.endswith(".weight") else ckv_b)[bi // self.ckv_group].append((bi, n, tuple(shape)))
+                else:
+                    groups[bi].append((n, tuple(shape)))
             else:
                 groups[depth].append((n, tuple(shape)))
+        for gi in range(self.n_ckv):
+            groups[depth + 1 + gi] = [(n, sh) for _, n, sh in sorted(ckv_w[gi])] + [(n, sh) for _, n, sh in sorted(ckv_b[gi])]
         self.groups = groups
         self.param = {}  # name -> (group, offset_in_group, numel, shape)
         self.group_numel = []  # padded, multiple of ALIGN*world
@@ -58,6 +77,41 @@ class Layout:
             self.shard_base.append(self.shard_base[-1] + self.shard_numel[g])
         self.full_total = self.full_base[-1]
         self.shard_total = self.shard_base[-1]
+
+    @property
+    def n_groups(self):
+        return len(self.groups)
+
+    def ckv_of_block(self, i):
+        """(ckv group index gi, position j of block i inside it, blocks in the group) or None."""
+        if not self.ckv_group:
+            return None
+        gi = i // self.ckv_group
+        nb = min(self.ckv_group, self.depth - gi * self.ckv_group)
+        return gi, i - gi * self.ckv_group, nb
+
+    def ckv_ranges(self, gi):
+        """Full-buffer (start, rows, cols) of the stacked [nb*2h, Dc] weight of ckv group gi and (start, numel) of its
+        stacked bias (None when the blocks have no context_kv bias).  Contiguity is asserted."""
+        plist = self.groups[self.depth + 1 + gi]
+        ws = [(n, sh) for n, sh in plist if n.endswith(".weight")]
+        bs = [(n, sh) for n, sh in plist if n.endswith(".bias")]
+        g = self.depth + 1 + gi
+        start = self.full_base[g] + self.param[ws[0][0]][1]
+        rows, cols = ws[0][1]
+        pos = start
+        for n, sh in ws:
+            assert self.full_base[g] + self.param[n][1] == pos and sh == (rows, cols), "context_kv weights not contiguous"
+            pos += rows * cols
+        bias = None
+        if bs:
+            b0 = self.full_base[g] + self.param[bs[0][0]][1]
+            pos = b0
+            for n, sh in bs:
+                assert self.full_base[g] + self.param[n][1] == pos, "context_kv biases not contiguous"
+                pos += sh[0]
+            bias = (b0, pos - b0)
+        return (start, rows * len(ws), cols), bias
 
     def full_range(self, name):
         g, off, numel, _ = self.param[name]
@@ -89,7 +143,7 @@ class Layout:
 
 class FlatShards:
     def __init__(self, model, param_dtype=torch.bfloat16, reduce_dtype=torch.float32, process_group=None,
-                 device=None):
+                 device=None, ckv_group=None):
         assert param_dtype == torch.bfloat16 and reduce_dtype == torch.float32, \
             "the CUDA path computes in bf16 and reduces gradients in fp32 (train.py:323-325)"
         self.pg = process_group
@@ -101,7 +155,13 @@ class FlatShards:
             device = named[0][1].device
         self.device = torch.device(device)
         self.depth = model.depth
-        self.layout = Layout([(n, p.shape) for n, p in named], model.depth, self.world)
+        if ckv_group is None:
+            # one grouped GEMM for the whole model at world size 1; groups of 4 blocks when sharded, so their gradient
+            # reduce-scatters still overlap the backward of the blocks that follow (env VDS_CKV_GROUP overrides; 0 = off)
+            ckv_group = int(os.environ.get("VDS_CKV_GROUP", model.depth if self.world == 1 else 4))
+        has_ckv = any(".context_kv." in n for n, _ in named)
+        self.layout = Layout([(n, p.shape) for n, p in named], model.depth, self.world,
+                             ckv_group=ckv_group if has_ckv else 0)
         lay = self.layout
         f32 = dict(device=self.device, dtype=torch.float32)
         b16 = dict(device=self.device, dtype=torch.bfloat16)
@@ -134,7 +194,7 @@ class FlatShards:
         self._seen_version = -1
         self.use_cuda = self.device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1) if self.use_cuda else None
-        self.ag_events = [None] * (self.depth + 1)
+        self.ag_events = [None] * self.layout.n_groups
         self.rs_events = []
         self._fresh = False
         self._gather_pending = False
@@ -191,7 +251,7 @@ class FlatShards:
     def gather_params(self):
         """All-gather every group's bf16 shard on the side stream (root group first, then block 0, 1, ...)."""
         self._gather_pending = False
-        order = [self.depth] + list(range(self.depth))
+        order = self.group_order()
         if self.world == 1:
             return  # shard16 aliases full16
         if not self.use_cuda:
@@ -209,6 +269,29 @@ class FlatShards:
                 ev = torch.cuda.Event()
                 ev.record(self.comm_stream)
                 self.ag_events[g] = ev
+
+    def group_order(self):
+        """Order in which the forward first touches the groups: root, then per block its ckv group (if it opens one) and
+        the block itself."""
+        lay = self.layout
+        order = [self.depth]
+        for i in range(self.depth):
+            c = lay.ckv_of_block(i)
+            if c is not None and c[1] == 0:
+                order.append(self.depth + 1 + c[0])
+            order.append(i)
+        return order
+
+    def ckv_views(self, gi):
+        """(stacked bf16 weight [nb*2h, Dc], stacked bf16 bias or None, fp32 grad of the weight, fp32 grad of the bias)
+        of ckv group gi, as views of the gathered / gradient buffers."""
+        (ws, rows, cols), bias = self.layout.ckv_ranges(gi)
+        W = self.full16[ws:ws + rows * cols].view(rows, cols)
+        gW = self.gfull[ws:ws + rows * cols].view(rows, cols)
+        if bias is None:
+            return W, None, gW, None
+        b0, bn = bias
+        return W, self.full16[b0:b0 + bn], gW, self.gfull[b0:b0 + bn]
 
     def mark_dirty(self):
         self._seen_version = -1
@@ -260,6 +343,9 @@ class FlatShards:
     def block_backward_done(self, i):
         self._reduce_group(i)
 
+    def ckv_backward_done(self, gi):
+        self._reduce_group(self.depth + 1 + gi)
+
     def end_backward(self):
         self._reduce_group(self.depth)
         if self.use_cuda:
@@ -283,7 +369,7 @@ class FlatShards:
         out = {}
         if self.world == 1:
             full = None
-        for g in range(self.depth + 1):
+        for g in range(lay.n_groups):
             fs, ss = self._group_slices(g)
             buf = torch.empty(lay.group_numel[g], device=self.device, dtype=torch.float32)
             self._all_gather(buf, self.master[ss].contiguous())
