@@ -275,6 +275,8 @@ class TrainRun:
 
     def close(self):
         import torch
+        if self.stepper is not None:
+            self.stepper.close()
         self.stepper = None
         hook = getattr(self.model, "_post_step_hook", None)
         if hook is not None:

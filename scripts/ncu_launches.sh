@@ -1,10 +1,11 @@
 #!/bin/bash
 # launch list of one bench step, kernels issued eagerly (--eager: same kernels as the graphed default, countable per step)
-# (cold-cache, serialised: compare SHARES) -> gpurun_out/launches_$1.csv
-TAG=${1:-r1}
-EXTRA=${2:-}
-ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --eager --steps 1 --warmup 3 --no-cpu-baseline --no-graph-extra $EXTRA > gpurun_out/ncu_bench_$TAG.log 2>&1
+# (cold-cache, serialised: compare SHARES) -> gpurun_out/launches_$TAG.csv + gpurun_out/launch_summary_$TAG.txt
+# usage: scripts/ncu_launches.sh TAG [extra bench.py flags, e.g. --workload B]
+TAG=${1:-r2}
+shift
+ncu --metrics gpu__time_duration.sum --clock-control none -c 40000 --csv --log-file gpurun_out/launches_$TAG.csv \
+    python bench.py --eager --steps 1 --warmup 3 --no-cpu-baseline --no-extras "$@" > gpurun_out/ncu_bench_$TAG.log 2>&1
 python - <<PY
 import csv, collections, sys
 rows = list(csv.reader(open("gpurun_out/launches_$TAG.csv", errors="ignore")))
@@ -18,13 +19,13 @@ for r in rows:
     v = v / 1e3 if u in ("ns", "nsecond") else (v if u in ("us", "usecond") else v * 1e3)
     k = d["Kernel Name"].split("(")[0][:70]
     agg[k][0] += 1; agg[k][1] += v
-NS = 5  # 3 warm-up + 1 timed + 1 e2e step, identical work
+NS = max(1, agg.get("vds::adamw_kernel", [1])[0])   # one AdamW launch per step: the number of (identical) steps profiled
 for k in agg: agg[k][1] /= NS; agg[k][0] /= NS
 tot = sum(v[1] for v in agg.values())
 with open("gpurun_out/launch_summary_$TAG.txt", "w") as f:
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         line = f"{t/1e3:9.3f} ms {100*t/tot:5.1f}% n={n:7.1f} avg={t/n:8.1f} us  {k}"
         print(line); f.write(line + "\n")
-    f.write(f"total {tot/1e3:.3f} ms over {sum(v[0] for v in agg.values())} launches\n")
+    f.write(f"total {tot/1e3:.3f} ms over {sum(v[0] for v in agg.values())} launches / step ({NS} steps profiled)\n")
 print("total ms", tot / 1e3)
 PY

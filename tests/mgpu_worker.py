@@ -40,6 +40,9 @@ def data(rank, dev):
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    if os.environ.get("VDS_MGPU_DEBUG") == "1":
+        import faulthandler
+        faulthandler.dump_traceback_later(75, exit=False)     # where is every rank if the run wedges
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
@@ -111,6 +114,8 @@ def main():
               f"{NSTEPS} sharded steps vs single-GPU reference {worst:.6f}; {'OK' if ok else 'FAIL'}")
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.broadcast(flag, 0)
+    if stepper is not None:
+        stepper.close()      # a live CUDA graph holding NCCL kernels makes destroy_process_group wait forever
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
 

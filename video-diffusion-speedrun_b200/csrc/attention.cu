@@ -703,7 +703,7 @@ int g_attn_pair_mode = -1;               // vds_debug_attn_pair_mode: -1 = VDS_A
 
 int launch_attn_bwd_pairs(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
                           int64_t lddo, const AttnBwdParams& p0, int B, int nh, int Lq, int Lk, int pair_base, int n_pairs,
-                          int pairs_per_bh, cudaStream_t stream);   // attention_bwd2.cu
+                          int pairs_per_bh, int q_splits, float* compact, cudaStream_t stream);   // attention_bwd2.cu
 
 // tail balancing fix-up: compact fp32 [item][dk|dv][128][128] -> bf16 dk / dv tiles
 __global__ void __launch_bounds__(256) attn_bwd_tail_fixup_kernel(const float* __restrict__ compact, bf16* __restrict__ dk,
@@ -856,10 +856,8 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
     return VDS_OK;
   };
 
-  // CTA-pair kernel (attention_bwd2.cu) for the bulk of a self-attention-sized problem: whole waves of kv-tile pairs
-  // (2 adjacent tiles of one (b, head) per 2-CTA cluster); what is left — the pairs of the last, partly filled wave and
-  // the unpaired last tile when kv_tiles is odd — goes to the 1-CTA kernel with query-range splits.
-  // VDS_ATTN_PAIR=0 disables it, VDS_ATTN_PAIR=force uses it for every pair regardless of wave fill (tests).
+  // CTA-pair kernel (attention_bwd2.cu) for a self-attention-sized problem: 2 adjacent kv tiles of one (b, head) per
+  // 2-CTA cluster.  VDS_ATTN_PAIR=0 disables it, VDS_ATTN_PAIR=force uses it regardless of problem size (tests).
   int pair_mode = g_attn_pair_mode;
   if (pair_mode < 0) {
     static int env_mode = -1;
@@ -869,24 +867,43 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
     }
     pair_mode = env_mode;
   }
-  const int pairs_per_bh = kv_tiles / 2;
+  const int pairs_per_bh = (kv_tiles + 1) / 2;   // the last pair of a (b, head) has a phantom second tile when kv_tiles is odd
   const int total_pairs = pairs_per_bh * nh * B;
   const int clusters = sms / 2;
-  int pairs_main = 0;
-  if (pair_mode != 0 && q_splits == 1 && dk != nullptr && dv != nullptr) {
-    // auto: long query ranges only (>= 64 sub-tiles: the pair kernel's longer prologue / epilogue and the extra launch
-    // for the remainder cost more than the ~12 % it gains per sub-tile on short ones: measured at L = 2064)
-    if (pair_mode == 2) pairs_main = total_pairs;
-    else if (n_qsub >= 64) pairs_main = (total_pairs / clusters) * clusters;
+  bool use_pairs = false;
+  if (pair_mode != 0 && q_splits == 1 && dk != nullptr && dv != nullptr && kv_tiles >= 2) {
+    // auto: long query ranges only (>= 64 sub-tiles: the pair kernel's longer prologue / epilogue costs more than the
+    // ~12 % it gains per sub-tile on short ones: measured at L = 2064) and at least one full wave of pairs
+    use_pairs = pair_mode == 2 || (n_qsub >= 64 && total_pairs >= clusters);
   }
-  if (pairs_main > 0) {
-    if ((r = launch_attn_bwd_pairs(q, ldq, k, ldk, v, ldv, d_o, lddo, p, B, nh, Lq, Lk, 0, pairs_main, pairs_per_bh, st)))
+  if (use_pairs) {
+    // Whole waves of pairs run unsplit (bf16 dK / dV written directly).  The pairs of the last, partly filled wave are
+    // split `s` ways along the query range (fp32 red into the compact workspace + the bf16 fix-up), so that wave costs
+    // ceil(rem * s / clusters) / s instead of 1.
+    const int full_p = (total_pairs / clusters) * clusters;
+    int rem_p = total_pairs - full_p, main_p = full_p, tail_s = 1;
+    if (rem_p > 0) {
+      const bool can_split = tail_ws != nullptr && n_qsub >= 16 && (long long)rem_p * 2 * 2 * 128 * HD * 4 <= tail_ws_bytes;
+      double best = 1.0;
+      for (int s = 2; can_split && s <= 8 && s * 8 <= n_qsub; ++s) {
+        const double cost = (double)((rem_p * s + clusters - 1) / clusters) / s + 0.03 * s;   // + per-split prologue / atomics
+        if (cost < best - 0.05) { best = cost; tail_s = s; }
+      }
+      if (tail_s == 1) { main_p = total_pairs; rem_p = 0; }   // no split possible / worthwhile: one launch for everything
+    }
+    if (main_p > 0 &&
+        (r = launch_attn_bwd_pairs(q, ldq, k, ldk, v, ldv, d_o, lddo, p, B, nh, Lq, Lk, 0, main_p, pairs_per_bh, 1, nullptr, st)))
       return r;
-    p.rem_pair_base = pairs_main;
-    p.rem_pairs_per_bh = pairs_per_bh;
-    p.rem_pair_tiles = 2 * (total_pairs - pairs_main);
-    const int rem = p.rem_pair_tiles + ((kv_tiles & 1) ? nh * B : 0);
-    if (rem > 0 && (r = launch_items(rem, true))) return r;
+    if (rem_p > 0) {
+      cudaMemsetAsync(tail_ws, 0, (size_t)rem_p * 2 * 2 * 128 * HD * 4, st);
+      if ((r = launch_attn_bwd_pairs(q, ldq, k, ldk, v, ldv, d_o, lddo, p, B, nh, Lq, Lk, main_p, rem_p, pairs_per_bh, tail_s,
+                                     (float*)tail_ws, st)))
+        return r;
+      AttnBwdParams pf = p;   // fix-up: local item = 2 * (pair - main_p) + cta -> (b, head, kv tile); phantom tiles skip themselves
+      pf.rem_pair_base = main_p; pf.rem_pairs_per_bh = pairs_per_bh; pf.rem_pair_tiles = 2 * rem_p;
+      launch_k(attn_bwd_tail_fixup_kernel, 2 * rem_p, 256, 0, st, (const float*)tail_ws, (bf16*)dk, lddk, (bf16*)dv, lddv, pf, Lk);
+      VDS_CHECK_LAUNCH("attn_bwd_tail_fixup");
+    }
     return VDS_OK;
   }
   // 1-CTA kernel for everything: full waves in one launch, the remainder of the last wave split along the query range

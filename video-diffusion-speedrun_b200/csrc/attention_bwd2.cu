@@ -136,7 +136,12 @@ __device__ __forceinline__ uint32_t sw64_offset(uint32_t r, uint32_t c) { return
 
 struct AttnBwd2Params {
   AttnBwdParams p;
-  int pair_base, pairs_per_bh;   // this launch covers pairs [pair_base, pair_base + gridDim.x / 2); pair -> (b*nh + head, kv tiles 2j, 2j+1)
+  // This launch covers pairs [pair_base, pair_base + gridDim.x / (2 * q_splits)); pair -> (b*nh + head, kv tiles 2j, 2j+1),
+  // pairs_per_bh = ceil(kv_tiles / 2): the second tile of the last pair of a (b, head) may lie entirely past Lk (its loads
+  // are TMA zero-fill, its rows masked, nothing of it is written).  q_splits > 1: each cluster takes 1 / q_splits of the
+  // query range and adds its dK / dV tiles (fp32 red) into compact[(pair - pair_base) * 2 + cta][dk | dv][128][128].
+  int pair_base, pairs_per_bh, q_splits;
+  float* compact;
 };
 
 __global__ void __launch_bounds__(B2_THREADS, 1)
@@ -177,11 +182,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
-  const int pid = pp.pair_base + (blockIdx.x >> 1);
+  const int cluster_id = blockIdx.x >> 1;
+  const int pair_local = cluster_id / pp.q_splits, split = cluster_id % pp.q_splits;
+  const int pid = pp.pair_base + pair_local;
   const int bh = pid / pp.pairs_per_bh, pj = pid % pp.pairs_per_bh;
   const int head = bh % p.nh, b = bh / p.nh;
   const int kv0_pair = pj * 256, kv0 = kv0_pair + (int)crank * 128;
-  const int n_q = (p.Lq + QSUB - 1) / QSUB;
+  const int n_q_all = (p.Lq + QSUB - 1) / QSUB;
+  const int per_split = (n_q_all + pp.q_splits - 1) / pp.q_splits;
+  const int qt0 = split * per_split;                       // first query sub-tile of this cluster
+  const int n_q = max(0, min(n_q_all, qt0 + per_split) - qt0);
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 2);
@@ -237,7 +247,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int i = 0; i < n_q; ++i) {
         const int st = i & 1;
         const uint32_t us = (i >> 1) & 1;
-        const int q0 = i * QSUB;
+        const int q0 = (qt0 + i) * QSUB;
         {
           mbar_wait(rows_empty + 8 * st, us ^ 1u);
           arm(s_ready + 8 * st, 2 * B2_ROWS_STAGE);
@@ -406,13 +416,13 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     auto stat_fetch = [&](int k) -> float {
       float raw = 0.f;
       if (stat_thread) {
-        const int q = min(k * QSUB + (int)crank * 32 + srow, p.Lq - 1);
+        const int q = min((qt0 + k) * QSUB + (int)crank * 32 + srow, p.Lq - 1);
         asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(raw) : "l"(stat_src + q));
       }
       return raw;
     };
     auto stat_finish = [&](int k, float raw) -> float {
-      const int q = k * QSUB + (int)crank * 32 + srow;
+      const int q = (qt0 + k) * QSUB + (int)crank * 32 + srow;
       if (q >= p.Lq) return which == 0 ? -INFINITY : 0.f;        // padded query row: exp2(-inf) = 0
       return which == 0 ? -raw * inv_sl2 : -raw;
     };
@@ -558,7 +568,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (lead_thread) {
-          tma_reduce_add_4d(&tmDQ, sSTG, (int)crank * 64, i * QSUB + pass * 32, head, b);
+          tma_reduce_add_4d(&tmDQ, sSTG, (int)crank * 64, (qt0 + i) * QSUB + pass * 32, head, b);
           bulk_commit_group();
         }
       }
@@ -583,16 +593,26 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_ld32(t + c * 32, v);
       tmem_ld_wait();
       if (krow < p.Lk) {
-        bf16* dst = (which == 0 ? p.dk + ((long long)b * p.Lk + krow) * p.lddk
-                                : p.dv + ((long long)b * p.Lk + krow) * p.lddv) + head * HD + c * 32;
+        if (pp.q_splits == 1) {
+          bf16* dst = (which == 0 ? p.dk + ((long long)b * p.Lk + krow) * p.lddk
+                                  : p.dv + ((long long)b * p.Lk + krow) * p.lddv) + head * HD + c * 32;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * osc, __uint_as_float(v[g * 8 + 1]) * osc);
-          u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * osc, __uint_as_float(v[g * 8 + 3]) * osc);
-          u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * osc, __uint_as_float(v[g * 8 + 5]) * osc);
-          u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * osc, __uint_as_float(v[g * 8 + 7]) * osc);
-          *reinterpret_cast<uint4*>(dst + g * 8) = u;
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * osc, __uint_as_float(v[g * 8 + 1]) * osc);
+            u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * osc, __uint_as_float(v[g * 8 + 3]) * osc);
+            u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * osc, __uint_as_float(v[g * 8 + 5]) * osc);
+            u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * osc, __uint_as_float(v[g * 8 + 7]) * osc);
+            *reinterpret_cast<uint4*>(dst + g * 8) = u;
+          }
+        } else {   // partial sums over this cluster's query range: fp32 red into the compact workspace (fixed up to bf16 later)
+          float* dst = pp.compact + (((long long)pair_local * 2 + crank) * 2 + which) * (128 * HD) + r * HD + c * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
+                         "f"(__uint_as_float(v[g * 4]) * osc), "f"(__uint_as_float(v[g * 4 + 1]) * osc),
+                         "f"(__uint_as_float(v[g * 4 + 2]) * osc), "f"(__uint_as_float(v[g * 4 + 3]) * osc)
+                         : "memory");
         }
       }
     }
@@ -606,7 +626,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 // Launches the pair kernel on pairs [pair_base, pair_base + n_pairs) of the (b, head, kv-tile-pair) space.
 int launch_attn_bwd_pairs(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
                           int64_t lddo, const AttnBwdParams& p0, int B, int nh, int Lq, int Lk, int pair_base, int n_pairs,
-                          int pairs_per_bh, cudaStream_t stream) {
+                          int pairs_per_bh, int q_splits, float* compact, cudaStream_t stream) {
   CUtensorMap tq, tqr, tk, tv, tdo, tdor, tdq;
   int r;
   if ((r = make_tmap_tokens(&tq, q, ldq, Lq, nh, B, QSUB))) return r;
@@ -626,8 +646,10 @@ int launch_attn_bwd_pairs(const void* q, int64_t ldq, const void* k, int64_t ldk
   pp.p = p0;
   pp.pair_base = pair_base;
   pp.pairs_per_bh = pairs_per_bh;
+  pp.q_splits = q_splits < 1 ? 1 : q_splits;
+  pp.compact = compact;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * n_pairs);
+  cfg.gridDim = dim3(2 * n_pairs * pp.q_splits);
   cfg.blockDim = dim3(B2_THREADS);
   cfg.dynamicSmemBytes = B2_SMEM;
   cfg.stream = stream;

@@ -118,6 +118,16 @@ class GraphedTrainStep:
         self.launches_per_step = 0
         self._side = None
 
+    def close(self):
+        """Drops the captured graph (and its private memory pool).  Required before ``dist.destroy_process_group()``
+        at world size > 1: a live graph that contains NCCL kernels keeps the communicator busy and the destroy hangs."""
+        self.graph = None
+        self.loss = None
+        import gc
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def _refresh_scalars(self):
         st, sh, sw = self._engine.draw_rope_starts(self.model.rope, self.thw)   # consumes the CPU RNG like the reference
         # Fresh pinned staging tensors every step: torch's caching host allocator does not hand a block out again
