@@ -16,5 +16,6 @@ for _ in range(2):
     ops.attn_bwd(q, k, v, out, d_o, lse, B, nh, L, L, dq, dk=dk, dv=dv)
 torch.cuda.synchronize()
 PY
-ncu --set full --clock-control none --import-source on -k regex:attn_.wd_kernel -s 3 -c 2 -o gpurun_out/prof_attn_$TAG python /tmp/attn_one.py > gpurun_out/ncu_attn_$TAG.log 2>&1
+# second iteration: attn_fwd, attn_bwd2 (main, unsplit), attn_bwd2 (remainder, split), fix-up
+ncu --set full --clock-control none --import-source on -k regex:attn_ -s 5 -c 5 -o gpurun_out/prof_attn_$TAG python /tmp/attn_one.py > gpurun_out/ncu_attn_$TAG.log 2>&1
 ls -la gpurun_out/prof_attn_$TAG.ncu-rep

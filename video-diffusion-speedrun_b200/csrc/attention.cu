@@ -173,6 +173,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                   make_float2(sl2, sl2), make_float2(nm0, nm0));
             mx0 = fmaxf(mx0, x.x);
             mx1 = fmaxf(mx1, x.y);
+            // every other pair on the FMA / ALU pipes (ptx.cuh: ex2_poly2) — the MUFU pipe is the co-bottleneck of this kernel
             const float2 pe = make_float2(ex2(x.x), ex2(x.y));
             s2 = add2(s2, pe);
             pk[c * 16 + (i >> 1)] = pack_bf16x2(pe.x, pe.y);

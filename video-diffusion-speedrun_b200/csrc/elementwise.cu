@@ -191,17 +191,22 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_fwd_kernel(const NormArgs a) 
     for (int i = 0; i < NV; ++i)
       if (i * 32 + lane < ng) raw[rr][i] = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
   }
-  // modulation of the first row's sample (rows of one warp straddle samples at most once; handled below)
-  uint4 rsc[NV], rsh[NV], rw[NV];
+  // modulation of the first row's sample (rows of one warp straddle samples at most once; handled below), unpacked ONCE per
+  // warp: bf16(1 + scale) and shift per column are the same for every row of a sample, and the conversions (XU pipe) were
+  // a third of this kernel's issue slots when redone per row
+  uint4 opscp[NV], shfp[NV], wfp[NV];   // bf16 pairs
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     if (i * 32 + lane < ng) {
       const int c = (i * 32 + lane) * 8;
       if (a.scale != nullptr) {
-        rsc[i] = *reinterpret_cast<const uint4*>(a.scale + (long long)bidx[0] * a.mod_stride + c);
-        rsh[i] = *reinterpret_cast<const uint4*>(a.shift + (long long)bidx[0] * a.mod_stride + c);
+        float sc[8];
+        ld8(a.scale + (long long)bidx[0] * a.mod_stride + c, sc);
+        shfp[i] = *reinterpret_cast<const uint4*>(a.shift + (long long)bidx[0] * a.mod_stride + c);
+        opscp[i] = make_uint4(pack_bf16x2(1.0f + sc[0], 1.0f + sc[1]), pack_bf16x2(1.0f + sc[2], 1.0f + sc[3]),
+                              pack_bf16x2(1.0f + sc[4], 1.0f + sc[5]), pack_bf16x2(1.0f + sc[6], 1.0f + sc[7]));
       }
-      if (a.weight != nullptr) rw[i] = *reinterpret_cast<const uint4*>(a.weight + c);
+      if (a.weight != nullptr) wfp[i] = *reinterpret_cast<const uint4*>(a.weight + c);
     }
   }
 #pragma unroll
@@ -232,22 +237,43 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_fwd_kernel(const NormArgs a) 
         for (int j = 0; j < 8; ++j) o[j] = v[i][j] * rstd;
         if (a.weight != nullptr) {
           float w[8];
-          unpack8f(rw[i], w);
+          unpack8f(wfp[i], w);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] *= w[j];
         }
         if (a.scale != nullptr) {
-          float sc[8], sh[8];
+          // bf16( bf16( bf16(n) * bf16(1 + scale) ) + shift ): the roundings run on packed pairs (one cvt per two elements)
+          uint4 nb;
+          nb.x = pack_bf16x2(o[0], o[1]); nb.y = pack_bf16x2(o[2], o[3]);
+          nb.z = pack_bf16x2(o[4], o[5]); nb.w = pack_bf16x2(o[6], o[7]);
+          float n8[8];
+          unpack8f(nb, n8);
           if (same) {
-            unpack8f(rsc[i], sc);
-            unpack8f(rsh[i], sh);
-          } else {
-            ld8(a.scale + (long long)bidx[rr] * a.mod_stride + c, sc);
-            ld8(a.shift + (long long)bidx[rr] * a.mod_stride + c, sh);
-          }
+            float os[8];
+            unpack8f(opscp[i], os);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o[j] = bf16_round(bf16_round(o[j]) * bf16_round(1.0f + sc[j])) + sh[j];
+            for (int j = 0; j < 8; ++j) n8[j] *= os[j];
+          } else {
+            float sc[8];
+            ld8(a.scale + (long long)bidx[rr] * a.mod_stride + c, sc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) n8[j] *= bf16_round(1.0f + sc[j]);
+          }
+          uint4 pb;
+          pb.x = pack_bf16x2(n8[0], n8[1]); pb.y = pack_bf16x2(n8[2], n8[3]);
+          pb.z = pack_bf16x2(n8[4], n8[5]); pb.w = pack_bf16x2(n8[6], n8[7]);
+          unpack8f(pb, o);
+          if (same) {
+            float sh[8];
+            unpack8f(shfp[i], sh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += sh[j];
+          } else {
+            float sh[8];
+            ld8(a.shift + (long long)bidx[rr] * a.mod_stride + c, sh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += sh[j];
+          }
         }
         st8(yr + c, o);
       }
@@ -272,7 +298,7 @@ struct NormBwdArgs {
 };
 
 template <int NV, bool HAS_W>
-__global__ void __launch_bounds__(256) rmsnorm_mod_bwd_kernel(const NormBwdArgs a) {
+__global__ void __launch_bounds__(256, (NV <= 2) ? 2 : 1) rmsnorm_mod_bwd_kernel(const NormBwdArgs a) {
   pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
   pdl_trigger();
   constexpr bool PF = false;  // one-row-ahead prefetch costs more in occupancy than it buys (measured)
@@ -306,6 +332,22 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_bwd_kernel(const NormBwdArgs 
       }
     }
   };
+  // per-column operands are the same for every row of this CTA (one sample per CTA): unpack / round them once
+  // (kept packed as bf16 pairs: 4 registers per group instead of 8, the kernel sits right at the 128-register occupancy step)
+  uint4 ops1p[NV], wfp[HAS_W ? NV : 1];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (i * 32 + lane < ng) {
+      const int c = (i * 32 + lane) * 8;
+      if (a.scale != nullptr) {
+        float sc[8];
+        ld8(a.scale + (long long)b * a.mod_stride + c, sc);
+        ops1p[i] = make_uint4(pack_bf16x2(1.0f + sc[0], 1.0f + sc[1]), pack_bf16x2(1.0f + sc[2], 1.0f + sc[3]),
+                              pack_bf16x2(1.0f + sc[4], 1.0f + sc[5]), pack_bf16x2(1.0f + sc[6], 1.0f + sc[7]));
+      }
+      if (HAS_W) wfp[HAS_W ? i : 0] = *reinterpret_cast<const uint4*>(a.weight + c);
+    }
+  }
   if (PF && r0 + warp < r1) fetch(r0 + warp);
   for (int r = r0 + warp; r < r1; r += 8) {
     if (!PF) fetch(r);
@@ -322,11 +364,13 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_bwd_kernel(const NormBwdArgs 
     for (int i = 0; i < NV; ++i) {
       if (i * 32 + lane < ng) {
         const int c = (i * 32 + lane) * 8;
-        float xv[8], dyv[8], w[8], sc[8];
+        float xv[8], dyv[8];
         unpack8f(cx[i], xv);
         unpack8f(cdy[i], dyv);
-        if (HAS_W) ld8(a.weight + c, w);
-        if (a.scale != nullptr) ld8(a.scale + (long long)b * a.mod_stride + c, sc);
+        float w[8], ops1[8];
+        if (HAS_W) unpack8f(wfp[HAS_W ? i : 0], w);
+        if (a.scale != nullptr) unpack8f(ops1p[i], ops1);
+        (void)c;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float n = xv[j] * rstd;
@@ -336,7 +380,7 @@ __global__ void __launch_bounds__(256) rmsnorm_mod_bwd_kernel(const NormBwdArgs 
           if (a.scale != nullptr) {
             acc_sc[i][j] += dyv[j] * xhat;
             acc_sh[i][j] += dyv[j];
-            dxhat = dyv[j] * bf16_round(1.0f + sc[j]);
+            dxhat = dyv[j] * ops1[j];
           }
           float d = dxhat;
           if (HAS_W) {
