@@ -156,6 +156,23 @@ def test_dit_b_and_xl_widths_vs_oracle(cuda_dev, hidden, heads, latent_thw, B):
     _compare(f"h={hidden}", loss, grads, rl, rg)
 
 
+def test_dit_xl_bench_shape_vs_oracle(cuda_dev):
+    """BASELINE config 4 at bench.py's exact per-block shapes (S_XL: h = 1152, 9 heads, B = 2 x [16,4,64,64] latents ->
+    L = 2064, context [2,512,4096]) at depth 2 against the fp32 oracle on the GPU: the size at which the 2-CTA GEMM with a
+    narrower last tile (N = 1152 / 3456), STORE_ROWDOT over 9 heads and the 17-tile attention backward are selected."""
+    cfg = dict(in_channels=16, patch_size=2, time_patch_size=2, hidden_size=1152, depth=2, num_heads=9, mlp_ratio=4.0,
+               cross_attn_input_size=4096, residual_v=True, train_bias_and_rms=False, use_rope=True)
+    model = build_model(cfg, 0, 1).to(cuda_dev)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 2 and not any(z in n for z in O.ZERO_INIT):
+                p.mul_(0.1)
+    latent, noise, context, t = [a.to(cuda_dev) for a in O.make_inputs(cfg, 2, (4, 64, 64), 512, 4096, 10)]
+    loss, _, grads = _cuda_step(model, latent, noise, context, t, 321, fused=True)
+    rl, _, rg = _oracle_step(model, cfg, latent, noise, context, t, 321, (2, 32, 32), torch.float32, cuda_dev)
+    _compare("S_XL bench shape (L=2064), depth 2", loss, grads, rl, rg)
+
+
 def test_sampling_width_forward_only(cuda_dev):
     """sample.py:43-53 model width (2048, 16 heads), bf16 module + bf16 RoPE tables, forward only, depth reduced."""
     cfg = dict(in_channels=16, patch_size=2, time_patch_size=2, hidden_size=2048, depth=2, num_heads=16,
