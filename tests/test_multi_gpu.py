@@ -20,7 +20,7 @@ def test_sharded_steps_match_single_gpu(world, graph, cfg):
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, VDS_MGPU_GRAPH=str(graph), VDS_MGPU_CFG=cfg)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                        "--master-addr", "127.0.0.1", "--master-port", str(29517 + world + 10 * graph),
+                        "--master-addr", "127.0.0.1", "--master-port", str(29517 + world + 10 * graph + 20 * (cfg == "debug")),
                         os.path.join(ROOT, "tests", "mgpu_worker.py")], capture_output=True, text=True, timeout=240,
                        env=env)
     print(r.stdout[-3000:], r.stderr[-3000:])
