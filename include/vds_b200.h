@@ -151,8 +151,14 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
                  int64_t ldkv_acc, int q_splits, int B, int nh, int Lq, int Lk, int head_dim, float scale,
                  void* tail_ws, int64_t tail_ws_bytes, void* stream);
 /* tail_ws (optional, q_splits == 1): fp32 workspace of vds_attn_bwd_tail_ws_bytes() bytes that lets the kernel split the
- * items of the partly-filled last wave along the query range (tail balancing); contents need no initialisation. */
+ * items of the partly-filled last wave along the query range (tail balancing).  It must be ZERO-FILLED once after it is
+ * allocated; every call hands it back zero-filled (the bf16 fix-up clears what it reads), so it is never memset per call. */
 int64_t vds_attn_bwd_tail_ws_bytes(int B, int nh, int Lk);
+/* host-only (no GPU work): the tail plan vds_attn_bwd uses for the CTA-pair kernel — `n_pairs` kv-tile pairs (less than one
+ * wave) of `n_qsub` 64-row query sub-tiles each, cut along the query range so that `clusters` SM pairs finish together.
+ * Writes up to `cap` pieces (pair | first sub-tile << 10 | sub-tile count << 21, longest first = launch order) and returns
+ * their number; 0 = the pairs run unsplit. */
+int vds_attn_bwd_tail_plan(int n_pairs, int n_qsub, int clusters, uint32_t* pieces, int cap);
 
 /* tuning aid: per-iteration clock64 trace of one CTA of attn_bwd (NULL disables). */
 int vds_debug_attn_bwd_trace(void* buf);

@@ -31,7 +31,8 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), f"{n} declared in include/vds_b200.h but not exported"
     assert L.vds_abi_version() == 1
     # every bound signature refers to a declared symbol and vice versa
-    bound = set(lib._SIGNATURES) | {"vds_last_error", "vds_abi_version", "vds_launch_count", "vds_attn_bwd_tail_ws_bytes"}
+    bound = set(lib._SIGNATURES) | {"vds_last_error", "vds_abi_version", "vds_launch_count", "vds_attn_bwd_tail_ws_bytes",
+                                     "vds_attn_bwd_tail_plan"}
     assert bound == set(names), (bound ^ set(names))
 
 

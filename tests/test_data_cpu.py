@@ -50,3 +50,46 @@ def test_attention_backward_query_split_model():
             v = qs(items, 1, 1, nq)
             assert 1 <= v <= max(1, 2 * nq)           # never more splits than 64-row sub-tiles
     assert qs(1, 1, 1, 1) <= 2
+
+
+def test_attn_bwd_tail_plan_covers_every_pair_once_and_balances():
+    """vds_attn_bwd_tail_plan (host-only C entry point): the pieces the CTA-pair attention backward cuts the pairs of its
+    partly filled last wave into.  Every pair's query range must be covered exactly once, no piece may be tiny, the pieces
+    come longest first, and the longest-first schedule on the SM pairs must beat both the unsplit launch and round 1's
+    uniform split."""
+    import ctypes
+    import heapq
+
+    import vds_b200  # noqa: F401
+    from vds_b200 import lib
+    L = lib.lib()
+    buf = (ctypes.c_uint32 * 256)()
+    for (P, nq, C) in [(42, 129, 74), (10, 129, 74), (1, 129, 74), (36, 129, 74), (20, 64, 74), (8, 33, 74), (73, 129, 74)]:
+        n = L.vds_attn_bwd_tail_plan(P, nq, C, buf, 256)
+        if n == 0:
+            assert P == 73      # splitting a nearly full wave does not pay
+            continue
+        pieces = [(buf[i] & 1023, (buf[i] >> 10) & 2047, buf[i] >> 21) for i in range(n)]
+        cover = {p: [] for p in range(P)}
+        for pair, q0, cnt in pieces:
+            assert 0 <= pair < P and cnt >= 8 and q0 + cnt <= nq
+            cover[pair].append((q0, cnt))
+        for p, segs in cover.items():
+            segs.sort()
+            pos = 0
+            for q0, cnt in segs:
+                assert q0 == pos
+                pos += cnt
+            assert pos == nq, (P, nq, p, segs)
+            assert len(segs) <= 3 or nq / len(segs) >= 8
+        assert [c for _, _, c in pieces] == sorted((c for _, _, c in pieces), reverse=True)
+        # greedy hand-out in launch order (what the block scheduler does), 10 sub-tile units of overhead per piece
+        slots = [0.0] * C
+        heapq.heapify(slots)
+        for _, _, cnt in pieces:
+            heapq.heappush(slots, heapq.heappop(slots) + cnt + 10.0)
+        makespan = max(slots)
+        assert makespan < nq + 10.0                       # better than unsplit
+        if (P, nq, C) == (42, 129, 74):                   # the debug-8k self-attention tail: uniform 3-way split = 2 x (43 + 10)
+            assert makespan <= 95.0
+    assert L.vds_attn_bwd_tail_plan(42, 129, 74, buf, 4) == 0      # too small a table: unsplit

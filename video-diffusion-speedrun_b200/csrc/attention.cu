@@ -15,6 +15,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.h"
 #include "ptx.cuh"
 #include "attn_common.cuh"
@@ -704,25 +707,82 @@ int g_attn_pair_mode = -1;               // vds_debug_attn_pair_mode: -1 = VDS_A
 
 int launch_attn_bwd_pairs(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
                           int64_t lddo, const AttnBwdParams& p0, int B, int nh, int Lq, int Lk, int pair_base, int n_pairs,
-                          int pairs_per_bh, int q_splits, float* compact, cudaStream_t stream);   // attention_bwd2.cu
+                          int pairs_per_bh, const uint32_t* pieces, int n_pieces, float* compact,
+                          cudaStream_t stream);   // attention_bwd2.cu
 
-// tail balancing fix-up: compact fp32 [item][dk|dv][128][128] -> bf16 dk / dv tiles
-__global__ void __launch_bounds__(256) attn_bwd_tail_fixup_kernel(const float* __restrict__ compact, bf16* __restrict__ dk,
+// Tail plan of the CTA-pair backward.  `P` pairs (fewer than one wave of `C` clusters) of `nq` query sub-tiles each are cut
+// into pieces along the query range so that `C` clusters finish together: the P * nq sub-tiles are laid out as one line,
+// cut into S equal ranges (cuts within `kMinPiece` of a pair boundary snap to it) and at every pair boundary; a range
+// crosses at most one boundary, so a pair ends up in <= 3 pieces.  S is the value whose longest-piece-first schedule on C
+// clusters (the order of the returned pieces == the order the hardware hands clusters to free SM pairs) finishes first,
+// with `kPieceOverhead` sub-tile units per piece for the prologue, the fp32 red of dK / dV and the exit (measured: 19.4 k
+// cycles against 2240 per sub-tile, scripts/bwd2_prof.py).  Piece = pair | first sub-tile << 10 | sub-tile count << 21.
+// Returns the number of pieces, 0 if splitting does not pay.
+static int attn_bwd_plan_tail(int P, int nq, int C, uint32_t* out, int cap) {
+  constexpr int kMinPiece = 8;
+  constexpr double kPieceOverhead = 10.0;
+  if (P <= 0 || C <= 0 || nq < 2 * kMinPiece || P >= 1024 || nq >= 2048) return 0;
+  const long long T = (long long)P * nq;
+  struct Piece { int pair, q0, n; };
+  std::vector<Piece> best, cur;
+  std::vector<long long> cuts;
+  std::vector<double> slot;
+  double best_cost = (double)((P + C - 1) / C) * (nq + kPieceOverhead);   // unsplit
+  const int s_max = (int)std::min<long long>(cap - P, T / kMinPiece);
+  for (int S = P; S <= s_max; ++S) {
+    cuts.clear();
+    for (int pb = 0; pb <= P; ++pb) cuts.push_back((long long)pb * nq);
+    for (int k = 1; k < S; ++k) {
+      long long c = (2 * k * T + S) / (2LL * S);                   // round(k * T / S)
+      const long long pb = ((2 * c + nq) / (2LL * nq)) * nq;         // nearest pair boundary
+      if (llabs(c - pb) < kMinPiece) c = pb;
+      cuts.push_back(c);
+    }
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    if ((int)cuts.size() - 1 > cap) continue;
+    cur.clear();
+    for (size_t i = 0; i + 1 < cuts.size(); ++i)
+      cur.push_back({(int)(cuts[i] / nq), (int)(cuts[i] % nq), (int)(cuts[i + 1] - cuts[i])});
+    std::stable_sort(cur.begin(), cur.end(), [](const Piece& a, const Piece& b) { return a.n > b.n; });
+    slot.assign(C, 0.0);
+    for (const Piece& pc : cur) {   // the next cluster goes to the SM pair that frees first
+      auto it = std::min_element(slot.begin(), slot.end());
+      *it += pc.n + kPieceOverhead;
+    }
+    const double cost = *std::max_element(slot.begin(), slot.end());
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = cur; }
+  }
+  for (size_t i = 0; i < best.size(); ++i)
+    out[i] = (uint32_t)best[i].pair | ((uint32_t)best[i].q0 << 10) | ((uint32_t)best[i].n << 21);
+  return (int)best.size();
+}
+
+// tail balancing fix-up: compact fp32 [item][dk|dv][128][128] -> bf16 dk / dv tiles; FIXUP_SPLIT CTAs per item (32 rows
+// each).  The workspace is handed back ZEROED (it is zero on entry of every vds_attn_bwd call: allocated zeroed by the
+// caller, restored here), which saves a memset node in front of every split launch.
+constexpr int FIXUP_SPLIT = 4;
+__global__ void __launch_bounds__(256) attn_bwd_tail_fixup_kernel(float* __restrict__ compact, bf16* __restrict__ dk,
                                                                   long long lddk, bf16* __restrict__ dv, long long lddv,
                                                                   const AttnBwdParams p, int Lk) {
   pdl_wait();      // inputs may come from the previous kernel (common.h: launch_k)
   pdl_trigger();
   int kv_tile, head, b;
-  attn_bwd_decode_item(p, blockIdx.x, b, head, kv_tile);
-  const float* src = compact + (long long)blockIdx.x * 2 * 128 * HD;
-  for (int idx = threadIdx.x; idx < 2 * 128 * (HD / 8); idx += blockDim.x) {
-    const int which = idx / (128 * (HD / 8));
-    const int rem = idx % (128 * (HD / 8));
-    const int r = rem / (HD / 8), c8 = rem % (HD / 8);
+  const int item = blockIdx.x / FIXUP_SPLIT, part = blockIdx.x % FIXUP_SPLIT;
+  attn_bwd_decode_item(p, item, b, head, kv_tile);
+  float* src = compact + (long long)item * 2 * 128 * HD;
+  constexpr int ROWS = 128 / FIXUP_SPLIT;
+  for (int idx = threadIdx.x; idx < 2 * ROWS * (HD / 8); idx += blockDim.x) {
+    const int which = idx / (ROWS * (HD / 8));
+    const int rem = idx % (ROWS * (HD / 8));
+    const int r = part * ROWS + rem / (HD / 8), c8 = rem % (HD / 8);
     const int krow = kv_tile * 128 + r;
-    if (krow >= Lk) continue;
-    const float4 a = *reinterpret_cast<const float4*>(src + (which * 128 + r) * HD + c8 * 8);
-    const float4 c = *reinterpret_cast<const float4*>(src + (which * 128 + r) * HD + c8 * 8 + 4);
+    if (krow >= Lk) continue;     // never written by the kernels either: stays zero
+    float4* s4 = reinterpret_cast<float4*>(src + (which * 128 + r) * HD + c8 * 8);
+    const float4 a = s4[0];
+    const float4 c = s4[1];
+    s4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    s4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     uint4 u;
     u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w); u.z = pack_bf16x2(c.x, c.y); u.w = pack_bf16x2(c.z, c.w);
     bf16* dst = (which == 0 ? dk + ((long long)b * Lk + krow) * lddk : dv + ((long long)b * Lk + krow) * lddv) + head * HD + c8 * 8;
@@ -773,6 +833,18 @@ int vds_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   launch_k(attn_fwd_kernel, grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream, tq, tk, tv, p);
   VDS_CHECK_LAUNCH("attn_fwd");
   return VDS_OK;
+}
+
+/* host-only: the tail plan of the CTA-pair backward for `n_pairs` pairs of `n_qsub` 64-row query sub-tiles on `clusters` SM
+ * pairs; writes up to `cap` pieces (pair | first sub-tile << 10 | count << 21, longest first) and returns their number
+ * (0: do not split).  Exported for the CPU tests of the schedule. */
+int vds_attn_bwd_tail_plan(int n_pairs, int n_qsub, int clusters, uint32_t* pieces, int cap) {
+  if (pieces == nullptr || cap <= 0) return 0;
+  uint32_t tmp[VDS_BWD2_MAX_PIECES];
+  const int n = attn_bwd_plan_tail(n_pairs, n_qsub, clusters, tmp, VDS_BWD2_MAX_PIECES);
+  if (n > cap) return 0;
+  for (int i = 0; i < n; ++i) pieces[i] = tmp[i];
+  return n;
 }
 
 int64_t vds_attn_bwd_tail_ws_bytes(int B, int nh, int Lk) {
@@ -846,13 +918,12 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
       VDS_CHECK_LAUNCH("attn_bwd");
       return VDS_OK;
     }
-    cudaMemsetAsync(tail_ws, 0, (size_t)rem * 2 * 128 * HD * 4, st);
     AttnBwdParams ps = p;
     ps.q_splits = tail_s; ps.compact_acc = (float*)tail_ws;
     if (p.rem_pair_base >= 0) ps.dbg = nullptr;   // the trace buffer belongs to the pair kernel of this call
     launch_k(attn_bwd_kernel, rem * tail_s, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, tdq, ps);
     VDS_CHECK_LAUNCH("attn_bwd");
-    launch_k(attn_bwd_tail_fixup_kernel, rem, 256, 0, st, (const float*)tail_ws, (bf16*)dk, lddk, (bf16*)dv, lddv, ps, Lk);
+    launch_k(attn_bwd_tail_fixup_kernel, rem * FIXUP_SPLIT, 256, 0, st, (float*)tail_ws, (bf16*)dk, lddk, (bf16*)dv, lddv, ps, Lk);
     VDS_CHECK_LAUNCH("attn_bwd_tail_fixup");
     return VDS_OK;
   };
@@ -878,31 +949,38 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
     use_pairs = pair_mode == 2 || (n_qsub >= 64 && total_pairs >= clusters);
   }
   if (use_pairs) {
-    // Whole waves of pairs run unsplit (bf16 dK / dV written directly).  The pairs of the last, partly filled wave are
-    // split `s` ways along the query range (fp32 red into the compact workspace + the bf16 fix-up), so that wave costs
-    // ceil(rem * s / clusters) / s instead of 1.
+    // Whole waves of pairs run unsplit (bf16 dK / dV written directly).  The pairs of the last, partly filled wave are cut
+    // into pieces along the query range (attn_bwd_plan_tail; fp32 red into the compact workspace + the bf16 fix-up) so that
+    // all clusters finish together.
     const int full_p = (total_pairs / clusters) * clusters;
-    int rem_p = total_pairs - full_p, main_p = full_p, tail_s = 1;
+    int rem_p = total_pairs - full_p, main_p = full_p, n_pieces = 0;
+    uint32_t pieces[VDS_BWD2_MAX_PIECES];
     if (rem_p > 0) {
       const bool can_split = tail_ws != nullptr && n_qsub >= 16 && (long long)rem_p * 2 * 2 * 128 * HD * 4 <= tail_ws_bytes;
-      double best = 1.0;
-      for (int s = 2; can_split && s <= 8 && s * 8 <= n_qsub; ++s) {
-        const double cost = (double)((rem_p * s + clusters - 1) / clusters) / s + 0.03 * s;   // + per-split prologue / atomics
-        if (cost < best - 0.05) { best = cost; tail_s = s; }
+      if (can_split) n_pieces = attn_bwd_plan_tail(rem_p, n_qsub, clusters, pieces, VDS_BWD2_MAX_PIECES);
+      static const int uni = getenv("VDS_BWD2_UNIFORM") ? atoi(getenv("VDS_BWD2_UNIFORM")) : 0;   // tuning switch: uniform s-way split
+      if (can_split && uni > 1 && rem_p * uni <= VDS_BWD2_MAX_PIECES) {
+        const int per = (n_qsub + uni - 1) / uni;
+        n_pieces = 0;
+        for (int pr = 0; pr < rem_p; ++pr)
+          for (int sp = 0; sp < uni; ++sp)
+            pieces[n_pieces++] = (uint32_t)pr | ((uint32_t)(sp * per) << 10) | ((uint32_t)std::min(per, n_qsub - sp * per) << 21);
       }
-      if (tail_s == 1) { main_p = total_pairs; rem_p = 0; }   // no split possible / worthwhile: one launch for everything
+      if (n_pieces == 0) { main_p = total_pairs; rem_p = 0; }   // no split possible / worthwhile: one launch for everything
     }
+    static const bool prof_tail = getenv("VDS_B2_PROF_TAIL") != nullptr;   // tuning: the trace buffer goes to the split launch only
+    AttnBwdParams pm = p;
+    if (prof_tail && rem_p > 0) pm.dbg = nullptr;
     if (main_p > 0 &&
-        (r = launch_attn_bwd_pairs(q, ldq, k, ldk, v, ldv, d_o, lddo, p, B, nh, Lq, Lk, 0, main_p, pairs_per_bh, 1, nullptr, st)))
+        (r = launch_attn_bwd_pairs(q, ldq, k, ldk, v, ldv, d_o, lddo, pm, B, nh, Lq, Lk, 0, main_p, pairs_per_bh, nullptr, 0, nullptr, st)))
       return r;
     if (rem_p > 0) {
-      cudaMemsetAsync(tail_ws, 0, (size_t)rem_p * 2 * 2 * 128 * HD * 4, st);
-      if ((r = launch_attn_bwd_pairs(q, ldq, k, ldk, v, ldv, d_o, lddo, p, B, nh, Lq, Lk, main_p, rem_p, pairs_per_bh, tail_s,
+      if ((r = launch_attn_bwd_pairs(q, ldq, k, ldk, v, ldv, d_o, lddo, p, B, nh, Lq, Lk, main_p, rem_p, pairs_per_bh, pieces, n_pieces,
                                      (float*)tail_ws, st)))
         return r;
       AttnBwdParams pf = p;   // fix-up: local item = 2 * (pair - main_p) + cta -> (b, head, kv tile); phantom tiles skip themselves
       pf.rem_pair_base = main_p; pf.rem_pairs_per_bh = pairs_per_bh; pf.rem_pair_tiles = 2 * rem_p;
-      launch_k(attn_bwd_tail_fixup_kernel, 2 * rem_p, 256, 0, st, (const float*)tail_ws, (bf16*)dk, lddk, (bf16*)dv, lddv, pf, Lk);
+      launch_k(attn_bwd_tail_fixup_kernel, 2 * rem_p * FIXUP_SPLIT, 256, 0, st, (float*)tail_ws, (bf16*)dk, lddk, (bf16*)dv, lddv, pf, Lk);
       VDS_CHECK_LAUNCH("attn_bwd_tail_fixup");
     }
     return VDS_OK;

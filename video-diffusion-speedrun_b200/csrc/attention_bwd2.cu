@@ -26,6 +26,8 @@
 // commits multicast to both CTAs' barriers; everything the issuer waits for arrives on the LEADER's barriers (remote
 // arrives from the follower).
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "attn_common.cuh"
 #include "common.h"
@@ -124,7 +126,7 @@ __device__ __forceinline__ uint32_t sw64_offset(uint32_t r, uint32_t c) { return
   do {                                                                                                          \
     if (p.dbg != nullptr && blockIdx.x < 2 && lane == 0) {                                                      \
       prof_acc[15] = clock64() - prof_t0;                                                                       \
-      for (int s_ = 0; s_ < 16; ++s_) p.dbg[((long long)crank * 3 + (role)) * 16 + s_] = prof_acc[s_];          \
+      for (int s_ = 0; s_ < 16; ++s_) p.dbg[((long long)crank * 4 + (role)) * 16 + s_] = prof_acc[s_];          \
     }                                                                                                           \
   } while (0)
 #else
@@ -133,23 +135,43 @@ __device__ __forceinline__ uint32_t sw64_offset(uint32_t r, uint32_t c) { return
 #define B2_PROF_STORE(role) do { } while (0)
 #endif
 #define B2_TRACE(slot, it) do { } while (0)
+// phase stamps of cluster 0 (PROF build): dbg[(crank * 4 + 3) * 16 + slot] = cycles since kernel entry
+#ifdef VDS_B2_PROF
+#define B2_STAMP(slot) do { if (p.dbg != nullptr && blockIdx.x < 2) p.dbg[((long long)crank * 4 + 3) * 16 + (slot)] = clock64() - t_entry; } while (0)
+#else
+#define B2_STAMP(slot) do { } while (0)
+#endif
 
 struct AttnBwd2Params {
   AttnBwdParams p;
-  // This launch covers pairs [pair_base, pair_base + gridDim.x / (2 * q_splits)); pair -> (b*nh + head, kv tiles 2j, 2j+1),
-  // pairs_per_bh = ceil(kv_tiles / 2): the second tile of the last pair of a (b, head) may lie entirely past Lk (its loads
-  // are TMA zero-fill, its rows masked, nothing of it is written).  q_splits > 1: each cluster takes 1 / q_splits of the
-  // query range and adds its dK / dV tiles (fp32 red) into compact[(pair - pair_base) * 2 + cta][dk | dv][128][128].
-  int pair_base, pairs_per_bh, q_splits;
+  // pair -> (b*nh + head, kv tiles 2j, 2j+1), pairs_per_bh = ceil(kv_tiles / 2): the second tile of the last pair of a
+  // (b, head) may lie entirely past Lk (its loads are TMA zero-fill, its rows masked, nothing of it is written).
+  //   n_pieces == 0: cluster c owns pair pair_base + c over the whole query range and writes bf16 dK / dV (TMA store when
+  //                  tma_dkdv, else per-thread stores).
+  //   n_pieces  > 0: cluster c owns PIECE c of the plan (attn_bwd_plan_tail): pieces[c] = pair_local | first sub-tile << 10 |
+  //                  sub-tile count << 21; it adds its dK / dV (fp32 red) into compact[pair_local * 2 + cta][dk | dv][128][128].
+  int pair_base, pairs_per_bh, n_pieces, tma_dkdv;
   float* compact;
+  uint32_t pieces[VDS_BWD2_MAX_PIECES];
 };
 
 __global__ void __launch_bounds__(B2_THREADS, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQr,
                  const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                  const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDOr,
-                 const __grid_constant__ CUtensorMap tmDQ, const AttnBwd2Params pp) {
+                 const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDK,
+                 const __grid_constant__ CUtensorMap tmDV, const __grid_constant__ AttnBwd2Params pp) {
   const AttnBwdParams& p = pp.p;
+#ifdef VDS_B2_PROF
+  const long long t_entry = clock64();
+  // per-CTA timeline (every CTA of the launch): dbg[128 + 4 * blockIdx.x + {0: smid, 1: entry, 2: set-up done, 3: exit}] in ns
+  auto gtimer = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
+  if (threadIdx.x == 0 && p.dbg != nullptr) {
+    unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    p.dbg[128 + 4 * (long long)blockIdx.x] = sm;
+    p.dbg[128 + 4 * (long long)blockIdx.x + 1] = gtimer();
+  }
+#endif
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -183,15 +205,16 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t crank = cluster_ctarank();
   const bool leader = crank == 0;
   const int cluster_id = blockIdx.x >> 1;
-  const int pair_local = cluster_id / pp.q_splits, split = cluster_id % pp.q_splits;
+  const bool split_mode = pp.n_pieces > 0;
+  const uint32_t piece = split_mode ? pp.pieces[cluster_id] : 0u;
+  const int pair_local = split_mode ? (int)(piece & 1023u) : cluster_id;
   const int pid = pp.pair_base + pair_local;
   const int bh = pid / pp.pairs_per_bh, pj = pid % pp.pairs_per_bh;
   const int head = bh % p.nh, b = bh / p.nh;
   const int kv0_pair = pj * 256, kv0 = kv0_pair + (int)crank * 128;
   const int n_q_all = (p.Lq + QSUB - 1) / QSUB;
-  const int per_split = (n_q_all + pp.q_splits - 1) / pp.q_splits;
-  const int qt0 = split * per_split;                       // first query sub-tile of this cluster
-  const int n_q = max(0, min(n_q_all, qt0 + per_split) - qt0);
+  const int qt0 = split_mode ? (int)((piece >> 10) & 2047u) : 0;     // first query sub-tile of this cluster
+  const int n_q = split_mode ? min((int)(piece >> 21), n_q_all - qt0) : n_q_all;
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 2);
@@ -223,6 +246,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / multicast commit / 2-SM TMA
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_gen;
+  if (threadIdx.x == 32) B2_STAMP(0);   // set-up done (barriers, TMEM, PDL wait, cluster sync)
+#ifdef VDS_B2_PROF
+  if (threadIdx.x == 0 && p.dbg != nullptr) p.dbg[128 + 4 * (long long)blockIdx.x + 2] = gtimer();
+#endif
   // TMEM columns (same in both CTAs): dV [0,128) | dK [128,256) | S^T buffers [256,320) [320,384) (afterwards, per half of
   // 32 query columns: bf16 P^T in 16 columns, dS^T in the next 16) | dP^T [384,448) | dQ^T [448,480): 128 lanes x 32
   // columns, lane % 64 = d of this CTA's half, lane / 64 = which 32 query columns
@@ -365,6 +392,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       __syncwarp();
       mbar_wait(kv_full, 0);
+      if (lane == 0) B2_STAMP(1);          // K / V tiles landed
       issue_s(0);
       issue_dp(0);
       if (n_q > 1) issue_s(1);
@@ -379,7 +407,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #endif
         if (i + 2 < n_q) issue_s_t(i + 2);
       }
+      if (lane == 0) B2_STAMP(2);          // last dV / dK issued
       issue_dq(n_q - 1);
+      if (lane == 0) B2_STAMP(3);          // last dQ^T issued
       B2_PROF_STORE(0);
     } else {
       // follower: relay "the leader's dS^T half has landed in my sDS slot 0" to the leader's issuer
@@ -573,7 +603,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
     }
-    if (lead_thread) bulk_wait_group0();
+    if (lead_thread) { B2_STAMP(6); bulk_wait_group0(); B2_STAMP(7); }   // last reduction issued / complete
     if (warp == 12) B2_PROF_STORE(2);
   }
   if (warp >= 4 && warp < 12) {
@@ -582,7 +612,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    if (threadIdx.x == 128) B2_STAMP(8);   // compute warps left the loop
     mbar_wait(mma_done, 0);
+    if (threadIdx.x == 128) B2_STAMP(4);   // dV / dK accumulators complete
     tc_fence_after();
     const int krow = kv0 + r;
     const uint32_t t = (which == 0 ? tDK : tDV) + lane_off;
@@ -592,20 +624,8 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint32_t v[32];
       tmem_ld32(t + c * 32, v);
       tmem_ld_wait();
-      if (krow < p.Lk) {
-        if (pp.q_splits == 1) {
-          bf16* dst = (which == 0 ? p.dk + ((long long)b * p.Lk + krow) * p.lddk
-                                  : p.dv + ((long long)b * p.Lk + krow) * p.lddv) + head * HD + c * 32;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * osc, __uint_as_float(v[g * 8 + 1]) * osc);
-            u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * osc, __uint_as_float(v[g * 8 + 3]) * osc);
-            u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * osc, __uint_as_float(v[g * 8 + 5]) * osc);
-            u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * osc, __uint_as_float(v[g * 8 + 7]) * osc);
-            *reinterpret_cast<uint4*>(dst + g * 8) = u;
-          }
-        } else {   // partial sums over this cluster's query range: fp32 red into the compact workspace (fixed up to bf16 later)
+      if (split_mode) {   // partial sums over this cluster's query range: fp32 red into the compact workspace (fixed up to bf16 later)
+        if (krow < p.Lk) {
           float* dst = pp.compact + (((long long)pair_local * 2 + crank) * 2 + which) * (128 * HD) + r * HD + c * 32;
 #pragma unroll
           for (int g = 0; g < 8; ++g)
@@ -614,20 +634,65 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                          "f"(__uint_as_float(v[g * 4 + 2]) * osc), "f"(__uint_as_float(v[g * 4 + 3]) * osc)
                          : "memory");
         }
+      } else if (pp.tma_dkdv) {
+        // the tile leaves through the K (dK) / V (dV) operand tile — every MMA that read it is complete (mma_done) — in the
+        // same two-halves SW128 image, then one TMA store per half: per-thread row stores are 32 partial sectors per
+        // warp instruction (measured: 6400 cycles for the 64 KiB of one CTA)
+        uint8_t* tile = gen + (which == 0 ? B2_OFF_K : B2_OFF_V);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * osc, __uint_as_float(v[g * 8 + 1]) * osc);
+          u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * osc, __uint_as_float(v[g * 8 + 3]) * osc);
+          u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * osc, __uint_as_float(v[g * 8 + 5]) * osc);
+          u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * osc, __uint_as_float(v[g * 8 + 7]) * osc);
+          st_tile8(tile, r, c * 32 + g * 8, u);
+        }
+      } else if (krow < p.Lk) {
+        bf16* dst = (which == 0 ? p.dk + ((long long)b * p.Lk + krow) * p.lddk
+                                : p.dv + ((long long)b * p.Lk + krow) * p.lddv) + head * HD + c * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * osc, __uint_as_float(v[g * 8 + 1]) * osc);
+          u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * osc, __uint_as_float(v[g * 8 + 3]) * osc);
+          u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * osc, __uint_as_float(v[g * 8 + 5]) * osc);
+          u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * osc, __uint_as_float(v[g * 8 + 7]) * osc);
+          *reinterpret_cast<uint4*>(dst + g * 8) = u;
+        }
+      }
+    }
+    if (!split_mode && pp.tma_dkdv) {
+      fence_proxy_async_smem();
+      named_bar_sync(3 + which, 128);
+      if (quad == 0 && lane == 0 && kv0 < p.Lk) {   // rows past Lk are clipped by the tensor map; a phantom tile stores nothing
+        const uint32_t tile = which == 0 ? sK : sV;
+        const CUtensorMap* tm = which == 0 ? &tmDK : &tmDV;
+        tma_store_4d(tm, tile, 0, kv0, head, b);
+        tma_store_4d(tm, tile + HALF_BYTES, 64, kv0, head, b);
+        bulk_commit_group();
+        bulk_wait_group0();
       }
     }
   }
+  if (threadIdx.x == 128) B2_STAMP(5);     // dK epilogue of warp 4 done
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 128) B2_STAMP(9);
   cluster_sync_all();   // nobody leaves while the peer may still store into / arrive on / multicast to this CTA
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  if (threadIdx.x == 32) B2_STAMP(10);
+#ifdef VDS_B2_PROF
+  if (threadIdx.x == 32 && p.dbg != nullptr) p.dbg[128 + 4 * (long long)blockIdx.x + 3] = gtimer();
+#endif
 }
 
-// Launches the pair kernel on pairs [pair_base, pair_base + n_pairs) of the (b, head, kv-tile-pair) space.
+// Launches the pair kernel on pairs [pair_base, pair_base + n_pairs) of the (b, head, kv-tile-pair) space: one cluster per
+// pair (n_pieces == 0) or one cluster per piece of the tail plan (pieces of those pairs along the query range).
 int launch_attn_bwd_pairs(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
                           int64_t lddo, const AttnBwdParams& p0, int B, int nh, int Lq, int Lk, int pair_base, int n_pairs,
-                          int pairs_per_bh, int q_splits, float* compact, cudaStream_t stream) {
-  CUtensorMap tq, tqr, tk, tv, tdo, tdor, tdq;
+                          int pairs_per_bh, const uint32_t* pieces, int n_pieces, float* compact, cudaStream_t stream) {
+  CUtensorMap tq, tqr, tk, tv, tdo, tdor, tdq, tdk, tdv;
   int r;
   if ((r = make_tmap_tokens(&tq, q, ldq, Lq, nh, B, QSUB))) return r;
   if ((r = make_tmap_tokens(&tqr, q, ldq, Lq, nh, B, 32))) return r;
@@ -636,20 +701,33 @@ int launch_attn_bwd_pairs(const void* q, int64_t ldq, const void* k, int64_t ldk
   if ((r = make_tmap_tokens(&tdo, d_o, lddo, Lq, nh, B, QSUB))) return r;
   if ((r = make_tmap_tokens(&tdor, d_o, lddo, Lq, nh, B, 32))) return r;
   if ((r = make_tmap_dq(&tdq, p0.dq_acc, p0.lddq, Lq, nh, B, 64, 32))) return r;
+  // bf16 dK / dV leave by TMA store when the buffers qualify (16-byte aligned base and row pitch), else by per-thread stores
+  static const bool tma_env = getenv("VDS_BWD2_TMA_OUT") == nullptr || strcmp(getenv("VDS_BWD2_TMA_OUT"), "0") != 0;   // tuning switch
+  const bool tma_out = tma_env && n_pieces == 0 && p0.dk != nullptr && p0.dv != nullptr && ((uintptr_t)p0.dk & 15) == 0 &&
+                       ((uintptr_t)p0.dv & 15) == 0 && p0.lddk % 8 == 0 && p0.lddv % 8 == 0;
+  tdk = tk; tdv = tv;
+  if (tma_out) {
+    if ((r = make_tmap_tokens(&tdk, p0.dk, p0.lddk, Lk, nh, B))) return r;
+    if ((r = make_tmap_tokens(&tdv, p0.dv, p0.lddv, Lk, nh, B))) return r;
+  }
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
     if (e != cudaSuccess) { set_error("attn_bwd2: smem attribute: %s", cudaGetErrorString(e)); return VDS_ERR_CUDA; }
     attr = true;
   }
+  VDS_CHECK_ARG(n_pieces >= 0 && n_pieces <= VDS_BWD2_MAX_PIECES, "attn_bwd2: %d pieces", n_pieces);
   AttnBwd2Params pp;
   pp.p = p0;
   pp.pair_base = pair_base;
   pp.pairs_per_bh = pairs_per_bh;
-  pp.q_splits = q_splits < 1 ? 1 : q_splits;
+  pp.n_pieces = n_pieces;
+  pp.tma_dkdv = tma_out ? 1 : 0;
   pp.compact = compact;
+  for (int i = 0; i < n_pieces; ++i) pp.pieces[i] = pieces[i];
+  for (int i = n_pieces; i < VDS_BWD2_MAX_PIECES; ++i) pp.pieces[i] = 0u;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * n_pairs * pp.q_splits);
+  cfg.gridDim = dim3(2 * (n_pieces > 0 ? n_pieces : n_pairs));
   cfg.blockDim = dim3(B2_THREADS);
   cfg.dynamicSmemBytes = B2_SMEM;
   cfg.stream = stream;
@@ -662,7 +740,7 @@ int launch_attn_bwd_pairs(const void* q, int64_t ldq, const void* k, int64_t ldk
   attrs[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
   cfg.attrs = attrs;
   cfg.numAttrs = 2;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_bwd2_kernel, tq, tqr, tk, tv, tdo, tdor, tdq, pp);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_bwd2_kernel, tq, tqr, tk, tv, tdo, tdor, tdq, tdk, tdv, pp);
   if (e != cudaSuccess) {
     set_error("attn_bwd2: cluster launch failed: %s", cudaGetErrorString(e));
     return VDS_ERR_CUDA;

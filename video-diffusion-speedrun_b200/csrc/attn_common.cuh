@@ -12,6 +12,7 @@ constexpr int QSUB = 64;   // query rows per backward sub-tile
 constexpr int HD = 128;
 constexpr int TILE_BYTES = 128 * HD * 2;  // 32 KiB: one 128 x 128 bf16 tile = two 64-wide SW128 halves
 constexpr int HALF_BYTES = TILE_BYTES / 2;
+#define VDS_BWD2_MAX_PIECES 256   // pieces of one tail plan of the CTA-pair backward (kernel-parameter table)
 
 // K-major operand tile (rows x 128 along the contraction): descriptor of 16-wide k-step kk
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kk) {

@@ -92,6 +92,8 @@ def lib():
         L.vds_launch_count.restype = ctypes.c_int64
         L.vds_attn_bwd_tail_ws_bytes.restype = ctypes.c_int64
         L.vds_attn_bwd_tail_ws_bytes.argtypes = [i32, i32, i32]
+        L.vds_attn_bwd_tail_plan.restype = ctypes.c_int      # returns a count, not an error code
+        L.vds_attn_bwd_tail_plan.argtypes = [i32, i32, i32, ctypes.POINTER(ctypes.c_uint32), i32]
         for name, argtypes in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = argtypes

@@ -279,11 +279,12 @@ _TAIL_WS = {}
 
 def _tail_ws(device, B, nh, Lk):
     """Tail-balancing workspace of vds_attn_bwd, one per device, grown (never shrunk) to the largest request so a
-    later, larger problem cannot silently lose tail balancing."""
+    later, larger problem cannot silently lose tail balancing.  Allocated zero-filled: the C side requires that once and
+    hands the workspace back zero-filled after every call (include/vds_b200.h)."""
     need = int(L.lib().vds_attn_bwd_tail_ws_bytes(B, nh, Lk))
     ws = _TAIL_WS.get(device)
     if ws is None or ws.numel() < need:
-        ws = torch.empty(need, device=device, dtype=torch.uint8)
+        ws = torch.zeros(need, device=device, dtype=torch.uint8)
         _TAIL_WS[device] = ws
     return ws
 
