@@ -421,7 +421,26 @@ def run_ours(args):
         loss = run.step(args.warmup + args.steps + 1 + i, bt["latent"], bt["context"])
         last["loss"] = loss.item()               # D2H read of the step's result inside the timed region
 
-    e2e_ms = timed(e2e_step, args.steps)
+    pipelined = run.stepper is not None and run.stepper.graph is not None
+
+    def stage_next(i):                           # host side of step i: wait for its H2D copy, fill the graph's inputs
+        bt = next(pf)
+        run.noise.copy_(bt["noise"], non_blocking=True)
+        torch.manual_seed(args.warmup + args.steps + 1 + i)   # RoPE offset draws, as TrainRun.step
+        run.stepper.stage(bt["latent"], bt["context"], run.t, run.noise)
+
+    def e2e_step_pipelined(i):
+        # software pipeline of a training loop on a captured step: launch step i (staged one iteration ago), prepare
+        # step i+1 on the host while the GPU computes (its copies queue behind the replay), then read step i's loss
+        loss = run.stepper.replay()
+        stage_next(i + 1)
+        last["loss"] = loss.item()               # D2H read of THIS step's result inside the timed region
+
+    if pipelined:
+        stage_next(0)
+        e2e_ms = timed(e2e_step_pipelined, args.steps)
+    else:
+        e2e_ms = timed(e2e_step, args.steps)
     h2d_per_step = sum(v.numel() * v.element_size() for v in (run.latent_h, run.context_h, run.noise_h))
     sampler.stop_flag = True
 
@@ -514,6 +533,9 @@ def run_ours(args):
                          "kernel_ms": kern_ms, "launches_timed": len(prof),
                          "kernel_share_of_step": kern_ms * depth / step_ms},
             "e2e": {"value": world * B * N / (e2e_ms * 1e-3), "unit": "latent tokens/s", "ms_per_step": e2e_ms,
+                    "pipeline": ("step i+1 staged on the host (H2D copy waited for, inputs / RoPE offsets / optimizer scalars "
+                                 "copied into the graph's buffers) behind the replay of step i; loss of step i read back "
+                                 "before step i+1 is launched") if pipelined else "stage, launch, read back, in sequence",
                     "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": 4, "last_loss": last.get("loss")},
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "cuda_graph": used_graph, "graph_error": graph_error, "issue_mode_probe": pick, "clocks": sampler.summary(),

@@ -49,6 +49,11 @@ enum vds_gemm_epilogue {
   VDS_EPI_GATE_RES = 3,  /* C = bf16(acc+bias?) ; C2 = bf16(aux + bf16(C*gate[b]))  model.py:139 */
   VDS_EPI_DGELU = 4,     /* C = bf16(acc * gelu'(aux))                                          */
   VDS_EPI_STORE_F32 = 5, /* C(fp32) = acc + bias?                                               */
+  VDS_EPI_QKV_ROPE = 7,  /* QKV projection of a DiT block, N = 3*heads*128 in "(k h d)" column order (model.py:124-134):
+                          * C[:, :2N/3] = RoPE(bf16(acc+bias?)) per 128-wide head with the cos / sin of table row (row % rows_per_batch) of rope_tab
+                          * (half-split rotation, model.py:266-275); C[:, 2N/3:] = v_pre = bf16(acc+bias?); with v0 != NULL
+                          * also C2[M, N/3] = bf16(lambda*v_pre) + bf16((1-lambda)*v0) (model.py:129-130).  2-CTA tile path
+                          * only: VDS_ERR_UNSUPPORTED otherwise (callers fall back to VDS_EPI_STORE + vds_qkv_post_fwd). */
   VDS_EPI_STORE_ROWDOT = 6 /* C = bf16(acc) ; rowdot[(b*(N/128) + n/128) * rows_per_batch + r] += sum over the 128-column
                             * head of C*aux (fp32; C2 = float* rowdot, zero-initialised by the caller): the dgrad GEMM
                             * that produces dO also emits delta = rowsum(dO*O) of the attention backward
@@ -80,6 +85,11 @@ typedef struct vds_gemm_args {
   int32_t tile_n; /* 0 = automatic (128 or 256), 128 = force 128-wide tiles (tuning / tests) */
   int32_t cluster; /* 0 = automatic (2-CTA cta_group::2 256x256 tiles when N % 256 == 0 and the grid fills the chip),
                       1 = 1-CTA tiles only, 2 = 1-CTA MMAs in 2-CTA clusters with multicast B (experiment) */
+  /* VDS_EPI_QKV_ROPE only (ABI version 2) */
+  const float* rope_tab; /* fp32 [rows_per_batch + 32, 4, 32]: vds_rope_pack output */
+  const void* v0;        /* bf16 [M, ldv0]: block 0's v (value residual), or NULL */
+  int64_t ldv0;
+  const void* lambda_;   /* bf16 scalar on the device (lambda_param), with v0 */
 } vds_gemm_args;
 
 int vds_gemm(const vds_gemm_args* args, void* stream);
@@ -99,6 +109,9 @@ int vds_unpatchify(const void* src, void* dst, int B, int C, int T, int H, int W
 int vds_rope_rows(const void* tcos, const void* tsin, int table_is_bf16, float* ocos, float* osin, int L, int D,
                   int n_reg, int Tp, int Hp, int Wp, int st, int sh, int sw, int hmax, int wmax, const int* starts_dev,
                   void* stream);   /* starts_dev != NULL: (t,h,w) offsets read from device memory (graph replays) */
+/* cos/sin rows [L, 64] -> the packed table VDS_EPI_QKV_ROPE reads by TMA: tab[l][s][0:16] = cos[l % L][16 s : 16 s + 16],
+ * tab[l][s][16:32] = sin[...] for l in [0, L + 32) (32 wrap-around rows: a 32-token box may cross a sample boundary). */
+int vds_rope_pack(const float* cos, const float* sin, float* tab, int L, void* stream);
 /* [cos(t f_i) | sin(t f_i)], bf16 out.                                                  model.py:12-22 */
 int vds_timestep_embedding(const void* t, void* out, int B, int dim, float max_period, void* stream);
 /* SiLU and its backward (nn.SiLU at model.py:90,320,340). */

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/vds_b200.h but not exported"
-    assert L.vds_abi_version() == 1
+    assert L.vds_abi_version() == 2
     # every bound signature refers to a declared symbol and vice versa
     bound = set(lib._SIGNATURES) | {"vds_last_error", "vds_abi_version", "vds_launch_count", "vds_attn_bwd_tail_ws_bytes",
                                      "vds_attn_bwd_tail_plan"}
@@ -59,7 +59,7 @@ def test_epilogue_enum_matches_header():
     from vds_b200 import lib
     hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "vds_b200.h")).read()
     enum = dict(re.findall(r"(VDS_EPI_[A-Z0-9_]+) = (\d+)", hdr))
-    assert len(enum) == 7
+    assert len(enum) == 8
     for name, val in enum.items():
         assert getattr(lib, name.replace("VDS_", "")) == int(val), name
     err = dict(re.findall(r"(VDS_ERR_[A-Z]+) = (-\d+)", hdr))

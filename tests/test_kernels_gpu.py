@@ -398,3 +398,42 @@ def test_loss_fwd_bwd(cuda_dev):
     assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item()) + 1e-7
     _close(lb, ref_b.detach(), tol=1e-5)
     _close(d_out, of.grad, tol=1e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M_B_L_nh_K,use_bias,mix", [((2, 8208, 4, 512), False, True), ((2, 8208, 4, 512), True, False),
+                                                     ((8, 272, 6, 768), False, True), ((2, 2064, 9, 1152), True, True)])
+def test_gemm_qkv_rope_epilogue(cuda_dev, M_B_L_nh_K, use_bias, mix):
+    """VDS_EPI_QKV_ROPE (RoPE + value residual inside the QKV GEMM epilogue, model.py:124-134) against (i) the plain GEMM +
+    the in-place qkv_post_fwd pass it replaces — same arithmetic, so bit for bit — and (ii) the fp32 reference rotation."""
+    from vds_b200 import ops
+    B, Lr, nh, K = M_B_L_nh_K
+    h = nh * 128
+    x = _r((B * Lr, K), cuda_dev, 31, 1.0)
+    w = _r((3 * h, K), cuda_dev, 32, K ** -0.5)
+    bias = _r((3 * h,), cuda_dev, 33, 0.5) if use_bias else None
+    ang = _r((Lr, 64), cuda_dev, 34, 3.0, torch.float32)
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    v0buf = _r((B * Lr, 3 * h), cuda_dev, 35)
+    v0 = v0buf[:, 2 * h:] if mix else None
+    lam = torch.tensor([0.4], device=cuda_dev).bfloat16() if mix else None
+    fused = ops.gemm_qkv_rope(x, w, bias, ops.rope_pack(cos, sin), Lr, v0=v0, v0_ld=v0.stride(0) if mix else 0, lam=lam)
+    assert fused is not None, "bench-sized QKV projections must take the 2-CTA fused path"
+    qkv_f, vmix_f = fused
+    qkv0 = ops.gemm(x, w, bias=bias)
+    qkv = qkv0.clone()
+    vmix = ops.qkv_post_fwd(qkv, B, Lr, h, nh, cos=cos, sin=sin, v0=v0, v0_ld=v0.stride(0) if mix else 0, lam=lam)
+    assert torch.equal(qkv_f[:, 2 * h:], qkv[:, 2 * h:])          # v_pre
+    if mix:
+        assert torch.equal(vmix_f, vmix)
+    else:
+        assert vmix_f is None
+    d = (qkv_f[:, :2 * h].float() - qkv[:, :2 * h].float()).abs()
+    assert d.max().item() <= 2 ** -6 * qkv[:, :2 * h].float().abs().max().item()    # at most an fma-contraction ulp apart
+    assert (d > 0).float().mean().item() < 1e-3
+    q = rearrange(qkv0[:, :h].view(B, Lr, h), "b l (h d) -> b h l d", h=nh)
+    rq = rearrange(_ref_rope(q, cos[None, None], sin[None, None]), "b h l d -> (b l) (h d)")
+    _close(qkv_f[:, :h], rq, tol=1e-2)
+    k = rearrange(qkv0[:, h:2 * h].view(B, Lr, h), "b l (h d) -> b h l d", h=nh)
+    rk = rearrange(_ref_rope(k, cos[None, None], sin[None, None]), "b h l d -> (b l) (h d)")
+    _close(qkv_f[:, h:2 * h], rk, tol=1e-2)

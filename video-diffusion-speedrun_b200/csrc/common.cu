@@ -98,6 +98,6 @@ int encode_tmap(CUtensorMap* tm, const void* base, int is_f32, int rank, const u
 
 extern "C" {
 const char* vds_last_error(void) { return vds::g_err; }
-int vds_abi_version(void) { return 1; }
+int vds_abi_version(void) { return 2; }
 int64_t vds_launch_count(void) { return vds::g_launches.load(); }
 }

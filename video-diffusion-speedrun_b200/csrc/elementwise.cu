@@ -117,6 +117,17 @@ __global__ void rope_rows_kernel(const TT* __restrict__ tcos, const TT* __restri
   }
 }
 
+// packed cos / sin table of the fused QKV epilogue (gemm2.cu: qkv_rope_epilogue_warp): [L + 32][4][16 cos | 16 sin]
+__global__ void rope_pack_kernel(const float* __restrict__ cos, const float* __restrict__ sin, float* __restrict__ tab, int L) {
+  pdl_wait();
+  pdl_trigger();
+  const long long total = (long long)(L + 32) * 128;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(i >> 7) % L, s = (int)(i >> 5) & 3, j = (int)i & 31;
+    tab[i] = j < 16 ? cos[l * 64 + s * 16 + j] : sin[l * 64 + s * 16 + j - 16];
+  }
+}
+
 // ------------------------------------------------------------------------------------- timestep emb
 // out[b, :half] = cos(t*f_i), out[b, half:] = sin(t*f_i), f_i = exp(-ln(max_period)*i/half)  (model.py:12-22)
 __global__ void timestep_embedding_kernel(const bf16* __restrict__ t, bf16* __restrict__ out, int B, int dim,
@@ -804,6 +815,14 @@ int vds_rope_rows(const void* tcos, const void* tsin, int table_is_bf16, float* 
                                                                    osin, L, D, n_reg, Tp, Hp, Wp, st, sh, sw, hmax,
                                                                    wmax, starts_dev);
   VDS_CHECK_LAUNCH("rope_rows");
+  return VDS_OK;
+}
+
+int vds_rope_pack(const float* cos, const float* sin, float* tab, int L, void* stream) {
+  VDS_CHECK_ARG(L > 0 && cos != nullptr && sin != nullptr && tab != nullptr, "rope_pack: bad arguments");
+  const long long total = (long long)(L + 32) * 128;
+  launch_k(rope_pack_kernel, min(ceil_div(total, 256), num_sms() * 16), 256, 0, (cudaStream_t)stream, cos, sin, tab, L);
+  VDS_CHECK_LAUNCH("rope_pack");
   return VDS_OK;
 }
 

@@ -260,6 +260,7 @@ static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
   p.gate = reinterpret_cast<const bf16*>(a.gate); p.gate_stride = a.gate_stride;
   p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
   p.remap_rows = a.remap_rows; p.remap_stride = a.remap_stride; p.remap_offset = a.remap_offset;
+  p.v0 = nullptr; p.ldv0 = 0; p.lambda = nullptr;   // (2-CTA QKV_ROPE epilogue only)
   p.dbg = nullptr;
 
   auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CL>;

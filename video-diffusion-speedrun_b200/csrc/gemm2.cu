@@ -32,9 +32,10 @@ constexpr int G2_MAX_STAGES = 6;
 template <int EPI>
 struct G2Cfg {
   static constexpr bool fused = EPI == VDS_EPI_BIAS_GELU || EPI == VDS_EPI_GATE_RES || EPI == VDS_EPI_DGELU ||
-                                EPI == VDS_EPI_STORE_ROWDOT;
-  static constexpr int stages = fused ? 5 : 6;
-  static constexpr int stg_warp = fused ? 8192 : 4096;
+                                EPI == VDS_EPI_STORE_ROWDOT || EPI == VDS_EPI_QKV_ROPE;
+  // QKV_ROPE: a third 4 KiB tile per warp receives the cos / sin rows of the warp's 32 tokens by TMA, for one more stage
+  static constexpr int stages = EPI == VDS_EPI_QKV_ROPE ? 4 : (fused ? 5 : 6);
+  static constexpr int stg_warp = EPI == VDS_EPI_QKV_ROPE ? 12288 : (fused ? 8192 : 4096);
 };
 constexpr int G2_SMEM = 6 * G2_STAGE + 8 * 4096 + 256 + 1024;   // same total for every variant
 // shared::cluster address of the same smem offset in CTA `rank` of this cluster
@@ -132,6 +133,7 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
         aux_phase ^= 1u;
 #pragma unroll
         for (int g = 0; g < 8; ++g) xa[g] = *reinterpret_cast<const uint4*>(S1 + stg_off(lane, g));
+        fence_proxy_async_smem();   // generic-proxy reads of S1 ordered before the async-proxy (TMA) refill issued below
         __syncwarp();
         // prefetch the aux tile of the next group (this tile's second group or the next tile's first)
         const bool more = gi == 0 || tile + tile_step < total_tiles;
@@ -261,6 +263,174 @@ __device__ __forceinline__ void fused_epilogue_warp(const GemmDev& p, const CUte
   }
   if (trace) {
     p.dbg[8] = c_tf; p.dbg[9] = c_ld; p.dbg[10] = c_aux; p.dbg[11] = c_math; p.dbg[12] = c_rd; p.dbg[13] = c_sts; p.dbg[14] = c_st;
+  }
+  if (lane == 0) bulk_wait_group0();   // all stores complete before the CTA may exit
+}
+
+// QKV projection epilogue (VDS_EPI_QKV_ROPE; model.py:124-134): a warp's 128-column half of the 256-wide tile is exactly one
+// 128-wide head of q, k or v ("(k h d)" column order), and the thread owns one token row of it.
+//   q / k heads: RoPE in fp32 on the bf16-rounded Linear output, half-split over the head (model.py:266-275): columns j and
+//                64 + j of the thread's row meet in registers.  The cos / sin values of the warp's 32 token rows arrive by
+//                TMA, 16 column pairs at a time, from the packed table of vds_rope_pack ([L + 32 wrap-around rows][4 steps]
+//                [16 cos | 16 sin] fp32: one 32-row x 128-byte box per step, also across a sample boundary) into a third
+//                staging tile T — per-thread loads of a 512-byte table row cost 32 line look-ups per warp instruction and
+//                made the epilogue 2.2 x the mainloop.  x1-half -> S0, x2-half -> S1, one TMA store each.
+//   v heads    : v_pre -> C; with the value residual (v0 != NULL) also v = bf16(l*v_pre) + bf16((1-l)*v0) -> C2 [M, N/3].
+// Replaces the in-place qkv_post_fwd pass over [B*L, 3h] (one read + one write of the whole qkv buffer per block).
+__device__ __forceinline__ void qkv_rope_epilogue_warp(const GemmDev& p, const CUtensorMap* tmC, const CUtensorMap* tmC2,
+                                                       const CUtensorMap* tmTab, uint8_t* S0, uint32_t tab_bar,
+                                                       uint32_t tmem_base, uint32_t tfull_bar0,
+                                                       uint32_t leader_tempty0, int tile0, int tile_step, int total_tiles,
+                                                       int m_pairs, int n_tiles, int crank, int q, int chalf, int lane) {
+  uint8_t* S1 = S0 + 4096;
+  uint8_t* T = S0 + 8192;
+  const uint32_t s0 = smem_u32(S0), s1 = smem_u32(S1), st = smem_u32(T);
+  const int h = p.N / 3;
+  const bool mix = p.v0 != nullptr;
+  float lam = 0.f, oml = 0.f;
+  if (mix) { lam = __bfloat162float(*p.lambda); oml = bf16_round(1.0f - lam); }
+  const bool has_bias = p.bias != nullptr;
+  uint32_t tab_phase = 0;
+  int it = 0;
+  for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+    const int acc = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1u;
+    const int row0 = ((tile % m_pairs) * 2 + crank) * BM + q * 32;
+    const int colh = ((tile / m_pairs) % n_tiles) * G2_BN + chalf * 128;   // first column of this warp's head
+    const bool col_ok = colh < p.N;          // false: the half past N of the last, narrower tile
+    const int which = colh / h;              // 0: q, 1: k, 2: v (warp-uniform)
+    const bool rot = col_ok && which < 2;
+    const int l0 = min(row0, p.M - 1) % p.rows_per_batch;    // table row of the warp's first token (the table wraps)
+    if (rot && lane == 0) {                  // cos / sin of step 0: in flight while the accumulator completes
+      mbar_expect_tx(tab_bar, 4096);
+      tma_load_3d(st, tmTab, tab_bar, 0, 0, l0);
+    }
+    mbar_wait(tfull_bar0 + 8u * acc, acc_phase);
+    tc_fence_after();
+    const uint32_t t_base = tmem_base + acc * G2_BN + (static_cast<uint32_t>(q * 32) << 16) + chalf * 128;
+    const int row = min(row0 + lane, p.M - 1);
+    auto release_acc = [&]() {               // last TMEM read of this accumulator buffer is complete
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
+    };
+    auto staging_free = [&]() {              // the TMA stores issued from S0 / S1 have finished reading them
+      if (lane == 0) bulk_wait_group_read0();
+      __syncwarp();
+    };
+    if (!col_ok) {
+      release_acc();
+    } else if (which < 2) {
+      // No control flow between a tcgen05.ld and its wait::ld: with the asynchronous destination registers live across the
+      // table barrier's spin loop ptxas placed register moves of them ahead of the wait (intermittently stale elements).
+      staging_free();
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {          // 16 column pairs (j, 64 + j) per step
+        uint4 b1[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)}, b2[2] = {b1[0], b1[0]};
+        if (has_bias) {
+          b1[0] = __ldg(reinterpret_cast<const uint4*>(p.bias + colh + s * 16));
+          b1[1] = __ldg(reinterpret_cast<const uint4*>(p.bias + colh + s * 16 + 8));
+          b2[0] = __ldg(reinterpret_cast<const uint4*>(p.bias + colh + 64 + s * 16));
+          b2[1] = __ldg(reinterpret_cast<const uint4*>(p.bias + colh + 64 + s * 16 + 8));
+        }
+        mbar_wait(tab_bar, tab_phase);
+        tab_phase ^= 1u;
+        uint32_t xa[16], xb[16];
+        tmem_ld16(t_base + s * 16, xa);
+        tmem_ld16(t_base + 64 + s * 16, xb);
+        float c[16], sv[16];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {     // (overlaps the TMEM read)
+          const float4 cc = *reinterpret_cast<const float4*>(T + stg_off(lane, ch));
+          const float4 ss = *reinterpret_cast<const float4*>(T + stg_off(lane, 4 + ch));
+          c[ch * 4] = cc.x; c[ch * 4 + 1] = cc.y; c[ch * 4 + 2] = cc.z; c[ch * 4 + 3] = cc.w;
+          sv[ch * 4] = ss.x; sv[ch * 4 + 1] = ss.y; sv[ch * 4 + 2] = ss.z; sv[ch * 4 + 3] = ss.w;
+        }
+        tmem_ld_wait();
+        // The table reads above (generic proxy) must be ordered before the TMA write of the next step into the same tile
+        // (async proxy): without the proxy fence ptxas sank the last two LDS below the TMA issue, and behind a cold bias
+        // miss they returned the NEXT step's values (columns 12..15 of the first q tiles, intermittently).
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (s < 3) {
+          if (lane == 0) {                   // next step's table rows land while this step is computed
+            mbar_expect_tx(tab_bar, 4096);
+            tma_load_3d(st, tmTab, tab_bar, 0, s + 1, l0);
+          }
+        } else {
+          release_acc();
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float bb1[8], bb2[8], y1[8], y2[8];
+          unpack8(b1[g], bb1);
+          unpack8(b2[g], bb2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float a1 = bf16_round(__uint_as_float(xa[g * 8 + j]) + bb1[j]);   // what the reference's RoPE sees
+            const float a2 = bf16_round(__uint_as_float(xb[g * 8 + j]) + bb2[j]);
+            const float cj = c[g * 8 + j], sj = sv[g * 8 + j];
+            y1[j] = a1 * cj + a2 * sj;
+            y2[j] = a1 * (-sj) + a2 * cj;
+          }
+          *reinterpret_cast<uint4*>(S0 + stg_off(lane, s * 2 + g)) = pack8(y1);
+          *reinterpret_cast<uint4*>(S1 + stg_off(lane, s * 2 + g)) = pack8(y2);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, s0, colh, row0);
+        tma_store_2d(tmC, s1, colh + 64, row0);
+        bulk_commit_group();
+      }
+    } else {
+      const bf16* v0row = mix ? p.v0 + (long long)row * p.ldv0 + (colh - 2 * h) : nullptr;
+#pragma unroll 1
+      for (int gi = 0; gi < 2; ++gi) {       // 64-column groups: v_pre -> S0, mixed v -> S1
+        staging_free();
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          uint4 b1[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)}, w0[2] = {b1[0], b1[0]};
+          if (has_bias) {
+            b1[0] = __ldg(reinterpret_cast<const uint4*>(p.bias + colh + gi * 64 + s * 16));
+            b1[1] = __ldg(reinterpret_cast<const uint4*>(p.bias + colh + gi * 64 + s * 16 + 8));
+          }
+          if (mix) {
+            w0[0] = __ldg(reinterpret_cast<const uint4*>(v0row + gi * 64 + s * 16));
+            w0[1] = __ldg(reinterpret_cast<const uint4*>(v0row + gi * 64 + s * 16 + 8));
+          }
+          uint32_t xa[16];
+          tmem_ld16(t_base + gi * 64 + s * 16, xa);
+          tmem_ld_wait();
+          if (s == 3 && gi == 1) release_acc();
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float bb[8], a8[8];
+            unpack8(b1[g], bb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a8[j] = __uint_as_float(xa[g * 8 + j]) + bb[j];
+            const uint4 vpre = pack8(a8);
+            *reinterpret_cast<uint4*>(S0 + stg_off(lane, s * 2 + g)) = vpre;
+            if (mix) {
+              float v8[8], o8[8];
+              unpack8(vpre, a8);
+              unpack8(w0[g], v8);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o8[j] = bf16_round(lam * a8[j]) + bf16_round(oml * v8[j]);
+              *reinterpret_cast<uint4*>(S1 + stg_off(lane, s * 2 + g)) = pack8(o8);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmC, s0, colh + gi * 64, row0);
+          if (mix) tma_store_2d(tmC2, s1, colh - 2 * h + gi * 64, row0);
+          bulk_commit_group();
+        }
+      }
+    }
   }
   if (lane == 0) bulk_wait_group0();   // all stores complete before the CTA may exit
 }
@@ -414,7 +584,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t leader_tempty0 = mapa_rank(tempty_bar(0), 0);
     int it = 0;
     long long e_wait = 0, e_busy = 0, e_tmem = 0, e_grp = 0;
-    if constexpr (G2Cfg<EPI>::fused) {
+    if constexpr (EPI == VDS_EPI_QKV_ROPE) {
+      qkv_rope_epilogue_warp(p, &tmC, &tmC2, &tmAux, smem_gen + G2_STAGES * G2_STAGE + (warp - 2) * G2Cfg<EPI>::stg_warp,
+                             aux_bar(warp - 2), tmem_base, tfull_bar(0), leader_tempty0, tile0, tile_step, total_tiles,
+                             m_pairs, n_tiles, crank, q, chalf, lane);
+      it = -1;
+    } else if constexpr (G2Cfg<EPI>::fused) {
       if (fast) {
         fused_epilogue_warp<EPI>(p, &tmC, &tmC2, &tmAux, smem_gen + G2_STAGES * G2_STAGE + (warp - 2) * 8192,
                                  aux_bar(warp - 2), tmem_base, tfull_bar(0), leader_tempty0, tile0, tile_step, total_tiles,
@@ -446,7 +621,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_tempty0 + 8u * acc);
-      } else if constexpr (EPI != VDS_EPI_STORE_ROWDOT) {   // (ROWDOT exists only as the fused fast path)
+      } else if constexpr (EPI != VDS_EPI_STORE_ROWDOT && EPI != VDS_EPI_QKV_ROPE) {   // (these exist only as fused fast paths)
         uint8_t* stg = smem_gen + G2_STAGES * G2_STAGE + (warp - 2) * 4096;   // 1024-byte aligned (TMA swizzle atom)
         constexpr int GROUPS = G2_BN / 128;
 #pragma unroll 1
@@ -520,7 +695,7 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
   // fused fast path: every bf16 operand / output of the epilogue reachable by TMA (no row remap, 16-byte aligned)
   CUtensorMap tmAux = tmA;
   int fast = 0;
-  if (G2Cfg<EPI>::fused && a.remap_rows == 0) {
+  if (G2Cfg<EPI>::fused && EPI != VDS_EPI_QKV_ROPE && a.remap_rows == 0) {
     auto ok = [](const void* ptr, long long ld) { return ptr != nullptr && ld % 8 == 0 && ((uintptr_t)ptr & 15) == 0; };
     uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M}, strides[1];
     uint32_t box[2] = {64, 32};
@@ -542,6 +717,31 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
       fast = 1;
     }
   }
+  if (EPI == VDS_EPI_QKV_ROPE) {
+    auto ok = [](const void* ptr, long long ld) { return ptr != nullptr && ld % 8 == 0 && ((uintptr_t)ptr & 15) == 0; };
+    const int h = a.N / 3;
+    const bool mix = a.v0 != nullptr;
+    if (a.N % 384 != 0 || a.rope_tab == nullptr || ((uintptr_t)a.rope_tab & 15) != 0 || a.rows_per_batch <= 0 || a.remap_rows != 0 ||
+        !ok(a.C, a.ldc) || (mix && (!ok(a.C2, a.ldc2) || a.lambda_ == nullptr || a.ldv0 % 8 != 0 || ((uintptr_t)a.v0 & 15) != 0))) {
+      set_error("gemm2: QKV_ROPE needs N = 3 * (heads * 128), the packed cos / sin table, rows_per_batch, TMA-able C (and C2, v0, lambda with the value residual)");
+      return VDS_ERR_UNSUPPORTED;
+    }
+    {   // packed table [rows_per_batch + 32][4][32] fp32 (vds_rope_pack): box = 32 token rows x one 128-byte step
+      uint64_t tdims[3] = {32, 4, (uint64_t)a.rows_per_batch + 32}, tstr[2] = {128, 512};
+      uint32_t tbox[3] = {32, 1, 32};
+      int r = encode_tmap(&tmAux, a.rope_tab, 1, 3, tdims, tstr, tbox, 1);
+      if (r) return r;
+    }
+    uint64_t dims[2] = {(uint64_t)a.N, (uint64_t)a.M}, strides[1] = {(uint64_t)a.ldc * 2};
+    uint32_t box[2] = {64, 32};
+    int r = encode_tmap_bf16(&tmC, a.C, 2, dims, strides, box);
+    if (r) return r;
+    if (mix) {
+      dims[0] = (uint64_t)h; strides[0] = (uint64_t)a.ldc2 * 2;
+      if ((r = encode_tmap_bf16(&tmC2, a.C2, 2, dims, strides, box))) return r;
+    }
+    fast = 1;
+  }
   if (EPI == VDS_EPI_STORE_ROWDOT) {
     if (!fast || a.C2 == nullptr || a.rows_per_batch <= 0 || a.N % 128 != 0) {
       set_error("gemm2: STORE_ROWDOT needs TMA-able C / aux, a rowdot buffer (C2), rows_per_batch and N %% 128 == 0");
@@ -561,6 +761,7 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
   p.gate = reinterpret_cast<const bf16*>(a.gate); p.gate_stride = a.gate_stride;
   p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : 1;
   p.remap_rows = a.remap_rows; p.remap_stride = a.remap_stride; p.remap_offset = a.remap_offset;
+  p.v0 = reinterpret_cast<const bf16*>(a.v0); p.ldv0 = a.ldv0; p.lambda = reinterpret_cast<const bf16*>(a.lambda_);
   p.dbg = g_gemm2_trace;
 
   auto kern = gemm2_kernel<A_MN, B_MN, EPI>;
@@ -611,6 +812,7 @@ int gemm2_dispatch(const vds_gemm_args& a, cudaStream_t s) {
       case VDS_EPI_STORE: return launch_gemm2<false, false, VDS_EPI_STORE>(a, s);
       case VDS_EPI_BIAS_GELU: return launch_gemm2<false, false, VDS_EPI_BIAS_GELU>(a, s);
       case VDS_EPI_GATE_RES: return launch_gemm2<false, false, VDS_EPI_GATE_RES>(a, s);
+      case VDS_EPI_QKV_ROPE: return launch_gemm2<false, false, VDS_EPI_QKV_ROPE>(a, s);
       default: return VDS_ERR_UNSUPPORTED;
     }
   }

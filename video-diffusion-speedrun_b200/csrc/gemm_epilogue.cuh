@@ -23,6 +23,7 @@ struct GemmDev {
   long long gate_stride;
   int rows_per_batch;
   int remap_rows, remap_stride, remap_offset;
+  const bf16* v0; long long ldv0; const bf16* lambda;       // QKV_ROPE value residual (v0 == nullptr: none)
   long long* dbg;   // tuning aid (nullptr in production)
 };
 

@@ -12,7 +12,11 @@ import torch
 from . import lib as L
 from . import ops
 
+import os
+
 N_REG = 16  # register tokens (model.py:316,362)
+# RoPE + value residual inside the QKV GEMM epilogue (VDS_EPI_QKV_ROPE); VDS_FUSE_QKV_ROPE=0: plain GEMM + qkv_post_fwd pass
+FUSE_QKV_ROPE = os.environ.get("VDS_FUSE_QKV_ROPE", "1") != "0"
 
 
 class ParamView:
@@ -107,6 +111,7 @@ def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise
         rope_starts = draw_rope_starts(model.rope, (Tp, Hp, Wp))
     cos, sin = ops.rope_rows(model.rope.freqs_hwt_cos, model.rope.freqs_hwt_sin, (Tp, Hp, Wp), rope_starts, N_REG,
                              starts_dev=rope_starts_dev)
+    rope_tab = ops.rope_pack(cos, sin) if FUSE_QKV_ROPE else None   # what the fused QKV epilogue reads by TMA
 
     # ---- time embedding : a5
     temb0 = ops.timestep_embedding(t_bf, h)
@@ -138,10 +143,20 @@ def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise
         # self attention
         n1, rstd1 = ops.rmsnorm_mod_fwd(X, B, Lr, h, scale=scale_sa, shift=shift_sa, weight=P.get(pre + "norm1.weight"),
                                         want_rstd=save)
-        qkv = ops.gemm(n1, P[pre + "qkv.weight"], bias=P.get(pre + "qkv.bias"))
         use_mix = residual_v and v0 is not None
-        vmix = ops.qkv_post_fwd(qkv, B, Lr, h, nh, cos=cos, sin=sin, v0=v0 if use_mix else None,
-                                v0_ld=v0.stride(0) if use_mix else 0, lam=P.get(pre + "lambda_param") if use_mix else None)
+        # RoPE + value residual in the QKV GEMM's epilogue (2-CTA tile path); small shapes: plain GEMM + in-place pass
+        fused = None
+        if rope_tab is not None:
+            fused = ops.gemm_qkv_rope(n1, P[pre + "qkv.weight"], P.get(pre + "qkv.bias"), rope_tab, Lr,
+                                      v0=v0 if use_mix else None, v0_ld=v0.stride(0) if use_mix else 0,
+                                      lam=P.get(pre + "lambda_param") if use_mix else None)
+        if fused is not None:
+            qkv, vmix = fused
+        else:
+            qkv = ops.gemm(n1, P[pre + "qkv.weight"], bias=P.get(pre + "qkv.bias"))
+            vmix = ops.qkv_post_fwd(qkv, B, Lr, h, nh, cos=cos, sin=sin, v0=v0 if use_mix else None,
+                                    v0_ld=v0.stride(0) if use_mix else 0,
+                                    lam=P.get(pre + "lambda_param") if use_mix else None)
         V = vmix if use_mix else qkv[:, 2 * h:]
         if v0 is None:
             v0 = V

@@ -39,11 +39,12 @@ class GemmArgs(ctypes.Structure):
         ("bias", vp), ("aux", vp), ("ldaux", i64),
         ("gate", vp), ("gate_stride", i64), ("rows_per_batch", i32),
         ("remap_rows", i32), ("remap_stride", i32), ("remap_offset", i32), ("tile_n", i32), ("cluster", i32),
+        ("rope_tab", vp), ("v0", vp), ("ldv0", i64), ("lambda_", vp),
     ]
 
 
 ERR_UNSUPPORTED = -3
-EPI_STORE, EPI_ACCUM_F32, EPI_BIAS_GELU, EPI_GATE_RES, EPI_DGELU, EPI_STORE_F32, EPI_STORE_ROWDOT = range(7)
+EPI_STORE, EPI_ACCUM_F32, EPI_BIAS_GELU, EPI_GATE_RES, EPI_DGELU, EPI_STORE_F32, EPI_STORE_ROWDOT, EPI_QKV_ROPE = range(8)
 
 fp = ctypes.POINTER(ctypes.c_float)
 
@@ -53,6 +54,7 @@ _SIGNATURES = {
     "vds_patchify": [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "vds_unpatchify": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "vds_rope_rows": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp],
+    "vds_rope_pack": [vp, vp, vp, i32, vp],
     "vds_timestep_embedding": [vp, vp, i32, i32, f32, vp],
     "vds_silu": [vp, vp, i64, vp],
     "vds_silu_bwd": [vp, vp, vp, i64, vp],

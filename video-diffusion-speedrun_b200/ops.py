@@ -96,6 +96,44 @@ def gemm(a, b, *, a_mn=False, b_mn=False, epilogue=L.EPI_STORE, out=None, out2=N
     return (out, out2) if out2 is not None else out
 
 
+def rope_pack(cos, sin):
+    """cos / sin rows [L, 64] fp32 -> the packed [L + 32, 4, 32] table the fused QKV epilogue reads by TMA (vds_rope_pack)."""
+    Lr = cos.shape[0]
+    assert cos.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous() and cos.shape == (Lr, 64) == sin.shape
+    tab = torch.empty((Lr + 32, 4, 32), device=cos.device, dtype=torch.float32)
+    L.check(L.lib().vds_rope_pack(_p(cos), _p(sin), _p(tab), Lr, _s()), "vds_rope_pack")
+    return tab
+
+
+def gemm_qkv_rope(x, w, bias, tab, rows_per_batch, v0=None, v0_ld=0, lam=None):
+    """qkv = x @ W^T (+ bias) with the block's RoPE (q, k heads) and value residual (v heads) applied in the GEMM epilogue
+    (model.py:124-134; VDS_EPI_QKV_ROPE).  Returns (qkv, vmix) — qkv[:, 2h:] holds v_pre, vmix is None without v0 — or None
+    when the shape has no 2-CTA tile path (the caller then runs the plain GEMM + qkv_post_fwd)."""
+    _chk_bf16(x, w, bias, v0, lam)
+    M, K = x.shape
+    N = w.shape[0]
+    assert tab.dtype == torch.float32 and tab.is_contiguous() and tab.shape == (rows_per_batch + 32, 4, 32)
+    qkv = torch.empty((M, N), device=x.device, dtype=torch.bfloat16)
+    vmix = torch.empty((M, N // 3), device=x.device, dtype=torch.bfloat16) if v0 is not None else None
+    args = L.GemmArgs()
+    args.A, args.B, args.lda, args.ldb = x.data_ptr(), w.data_ptr(), x.stride(0), w.stride(0)
+    args.M, args.N, args.K = M, N, K
+    args.epilogue, args.splits = L.EPI_QKV_ROPE, 1
+    args.C, args.ldc = qkv.data_ptr(), qkv.stride(0)
+    if vmix is not None:
+        args.C2, args.ldc2 = vmix.data_ptr(), vmix.stride(0)
+        args.v0, args.ldv0, args.lambda_ = v0.data_ptr(), v0_ld, lam.data_ptr()
+    if bias is not None:
+        args.bias = bias.data_ptr()
+    args.rope_tab = tab.data_ptr()
+    args.rows_per_batch = rows_per_batch
+    rc = L.lib().vds_gemm(ctypes.byref(args), _stream())
+    if rc == L.ERR_UNSUPPORTED:
+        return None
+    L.check(rc, "vds_gemm")
+    return qkv, vmix
+
+
 def gemm_dgrad_rowdot(dy, w, o, rowdot, rows_per_batch):
     """dX = dy @ W (dgrad, W [N_out, N_in] read MN-major) and, in the same epilogue, rowdot[b, head, r] += <dX_head, o_head>
     per 128-column head — the `delta` of the attention backward.  `rowdot`: zero-initialised fp32 [B, N_in/128,

@@ -154,13 +154,19 @@ class GraphedTrainStep:
             self.opt.step(gather=not sharded)    # sharded: the next step's graph gathers at its top
         return loss.view(())
 
-    def __call__(self, latent, context, t, noise, caption_dropout=CAPTION_DROPOUT):
+    def stage(self, latent, context, t, noise, caption_dropout=CAPTION_DROPOUT):
+        """Host side of one step: the inputs and the per-step scalars go into the graph's static buffers (stream-ordered
+        copies).  May be issued while the previous replay is still running — it queues behind it — so a training loop can
+        prepare step i+1 on the host while the GPU computes step i (``replay()`` launches what was staged last)."""
         self.latent.copy_(latent, non_blocking=True)
         self.context.copy_(context, non_blocking=True)
         drop_captions(self.context, caption_dropout, out=self.context)   # train.py:86-87, outside the graph
         self.t.copy_(t, non_blocking=True)
         self.noise.copy_(noise, non_blocking=True)
         self._refresh_scalars()
+
+    def replay(self):
+        """Runs the step on the staged inputs; returns the (static) loss tensor."""
         # The device copy of the optimizer scalars is installed only while this call captures / replays: a later eager
         # opt.step() (e.g. after falling back from the graph) must read lr / wd / bias corrections by value again.
         self.opt.hyper_dev = self.hyper_dev
@@ -168,6 +174,10 @@ class GraphedTrainStep:
             return self._run()
         finally:
             self.opt.hyper_dev = None
+
+    def __call__(self, latent, context, t, noise, caption_dropout=CAPTION_DROPOUT):
+        self.stage(latent, context, t, noise, caption_dropout)
+        return self.replay()
 
     def _run(self):
         if self.graph is None:
