@@ -772,21 +772,33 @@ __global__ void __launch_bounds__(256) attn_bwd_tail_fixup_kernel(float* __restr
   attn_bwd_decode_item(p, item, b, head, kv_tile);
   float* src = compact + (long long)item * 2 * 128 * HD;
   constexpr int ROWS = 128 / FIXUP_SPLIT;
-  for (int idx = threadIdx.x; idx < 2 * ROWS * (HD / 8); idx += blockDim.x) {
+  constexpr int ITERS = 2 * ROWS * (HD / 8) / 256;    // 8-element groups per thread: all loads issued before the first store
+  float4 a[ITERS], c[ITERS];
+  float4* s4[ITERS];
+  bf16* dst[ITERS];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int idx = it * 256 + threadIdx.x;
     const int which = idx / (ROWS * (HD / 8));
     const int rem = idx % (ROWS * (HD / 8));
     const int r = part * ROWS + rem / (HD / 8), c8 = rem % (HD / 8);
     const int krow = kv_tile * 128 + r;
+    s4[it] = nullptr;
     if (krow >= Lk) continue;     // never written by the kernels either: stays zero
-    float4* s4 = reinterpret_cast<float4*>(src + (which * 128 + r) * HD + c8 * 8);
-    const float4 a = s4[0];
-    const float4 c = s4[1];
-    s4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-    s4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    s4[it] = reinterpret_cast<float4*>(src + (which * 128 + r) * HD + c8 * 8);
+    dst[it] = (which == 0 ? dk + ((long long)b * Lk + krow) * lddk : dv + ((long long)b * Lk + krow) * lddv) + head * HD + c8 * 8;
+    a[it] = __ldcg(s4[it]);       // written by red.global (L2): read there
+    c[it] = __ldcg(s4[it] + 1);
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    if (s4[it] == nullptr) continue;
+    s4[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    s4[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
     uint4 u;
-    u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w); u.z = pack_bf16x2(c.x, c.y); u.w = pack_bf16x2(c.z, c.w);
-    bf16* dst = (which == 0 ? dk + ((long long)b * Lk + krow) * lddk : dv + ((long long)b * Lk + krow) * lddv) + head * HD + c8 * 8;
-    *reinterpret_cast<uint4*>(dst) = u;
+    u.x = pack_bf16x2(a[it].x, a[it].y); u.y = pack_bf16x2(a[it].z, a[it].w);
+    u.z = pack_bf16x2(c[it].x, c[it].y); u.w = pack_bf16x2(c[it].z, c[it].w);
+    *reinterpret_cast<uint4*>(dst[it]) = u;
   }
 }
 
