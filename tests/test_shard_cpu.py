@@ -130,6 +130,22 @@ def _worker(rank, world, port, out):
                 continue
             s, po, ln = flat.layout.shard_range(n, rank)
             assert torch.allclose(p.grad.flatten(), ref[n].flatten()[po:po + ln] * mean, rtol=1e-6, atol=1e-7), n
+        # 3b. a second backward without zero_grad accumulates into the reduced shard (gradient accumulation at W > 1)
+        flat.begin_backward()
+        for n in names:
+            flat.grad_views[n].copy_(ref[n] * (rank + 1) * 0.5)
+        for g in range(flat.depth):
+            flat.block_backward_done(g)
+        for gi in range(flat.layout.n_ckv):
+            flat.ckv_backward_done(gi)
+        flat.end_backward()
+        for n, p in m.named_parameters():
+            if n == "blocks.0.lambda_param":
+                continue
+            s, po, ln = flat.layout.shard_range(n, rank)
+            assert torch.allclose(p.grad.flatten(), ref[n].flatten()[po:po + ln] * mean * 1.5, rtol=1e-6, atol=1e-7), n
+        for p in m.parameters():
+            p.grad = None
         # 4. state_dict() returns full reference-shaped tensors
         sd = m.state_dict()
         for n in names:

@@ -224,6 +224,15 @@ class FlatShards:
     def _reduce_scatter_avg(self, out, inp):
         if self.world == 1:
             return
+        if getattr(self, "_accumulate", False):     # a second backward without zero_grad: out += reduce_scatter(inp)
+            tmp = torch.empty_like(out)
+            self._accumulate = False
+            try:
+                self._reduce_scatter_avg(tmp, inp)
+            finally:
+                self._accumulate = True
+            out.add_(tmp)
+            return
         if self.backend == "gloo":
             tmp = inp.clone()
             dist.all_reduce(tmp, group=self.pg)
@@ -318,9 +327,9 @@ class FlatShards:
         # zero_grad in between).  Frozen parameters never get a .grad here (end_backward), so one frozen / optimizer-less
         # tensor cannot pin the buffer in accumulate mode.
         self._accumulate = any(p.grad is not None for p in self.params.values() if p.requires_grad)
-        if self._accumulate and self.world > 1:
-            raise NotImplementedError("gradient accumulation over several backward passes needs world_size 1")
-        if not self._accumulate:
+        # W == 1: gfull IS the gradient (no reduce), accumulating = not zeroing it.  W > 1: gfull only holds this backward's
+        # local gradient; the reduced shard gshard (what .grad views) adds each backward's reduce-scatter (_reduce_group).
+        if not self._accumulate or self.world > 1:
             self.gfull.zero_()
         self.rs_events = []
 
