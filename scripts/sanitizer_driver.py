@@ -34,6 +34,13 @@ big = bf(40000, h)      # large enough for the 2-CTA path
 ops.gemm(big, w1, bias=b1)
 rowdot = torch.zeros((2, 4, 20000), device=dev, dtype=torch.float32)
 ops.gemm_dgrad_rowdot(big, bf(h, h), big, rowdot, 20000)
+# QKV projection with the fused RoPE / value-residual epilogue (2-CTA path), incl. a bias and a ragged last m-tile
+Lq, nhq = 5003, 4
+xq, wq, bq, v0q = bf(2 * Lq, h), bf(3 * nhq * 128, h), bf(3 * nhq * 128), bf(2 * Lq, nhq * 128)
+angq = torch.randn((Lq, 64), device=dev)
+tabq = ops.rope_pack(angq.cos().contiguous(), angq.sin().contiguous())
+assert ops.gemm_qkv_rope(xq, wq, bq, tabq, Lq, v0=v0q, v0_ld=nhq * 128, lam=torch.tensor([0.3], device=dev).bfloat16()) is not None
+assert ops.gemm_qkv_rope(xq, wq, None, tabq, Lq) is not None
 y, rstd = ops.rmsnorm_mod_fwd(x, 2, M // 2, h, scale=mod[:, h:2 * h], shift=mod[:, :h])
 dmod = torch.zeros((2, 9 * h), device=dev, dtype=torch.float32)
 ops.rmsnorm_mod_bwd(x, x, rstd, 2, M // 2, h, scale=mod[:, h:2 * h], dx_res=res, dscale=dmod[:, h:2 * h], dshift=dmod[:, :h])

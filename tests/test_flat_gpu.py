@@ -117,3 +117,49 @@ def test_graphed_train_step_matches_eager(cuda_dev):
             assert u1.abs().max().item() == 0, n
             continue
         assert cos_sim(u0, u1) > 0.98, (n, cos_sim(u0, u1))
+
+
+def test_graphed_step_stage_replay_pipeline(cuda_dev):
+    """`stage()` issued behind a running `replay()` (what bench.py's e2e leg and a pipelined training loop do) gives the
+    same losses as the one-call form: the staged copies queue behind the replay that still reads the old inputs, and the
+    static loss tensor of step i is read back before step i+1 is launched."""
+    from vds_b200 import train
+    from vds_b200.model import apply_fsdp
+    from vds_b200.optim import FusedAdamW
+    results = []
+    for pipelined in (False, True):
+        fx, cfg, model, (latent, noise, context, t) = golden_case("tiny_bias")
+        model = apply_fsdp(model.to(cuda_dev), torch.bfloat16, torch.float32)
+        groups, _ = model.get_mup_setup(2 ** -7, 1e-1, CONST)
+        opt = FusedAdamW(groups, betas=(0.95, 0.99), flat=model._flat)
+        latent, noise, context, t = [a.to(cuda_dev) for a in (latent, noise, context, t)]
+        batches = [(latent * (1.0 + 0.1 * i), context * (1.0 - 0.05 * i)) for i in range(6)]   # every step sees new inputs
+        stepper = train.GraphedTrainStep(model, opt, latent.shape, context.shape, device=cuda_dev, warmup=1)
+        losses = []
+        if not pipelined:
+            for i, (la, cx) in enumerate(batches):
+                torch.manual_seed(200 + i)
+                losses.append(stepper(la, cx, t, noise, caption_dropout=0.0).item())
+        else:
+            for i in range(2):                      # warm-up + capture through the one-call form
+                torch.manual_seed(200 + i)
+                losses.append(stepper(batches[i][0], batches[i][1], t, noise, caption_dropout=0.0).item())
+            assert stepper.graph is not None
+            torch.manual_seed(202)
+            stepper.stage(batches[2][0], batches[2][1], t, noise, caption_dropout=0.0)
+            for i in range(2, 6):
+                loss = stepper.replay()
+                if i + 1 < 6:                       # host side of the next step, queued behind the running replay
+                    torch.manual_seed(200 + i + 1)
+                    stepper.stage(batches[i + 1][0], batches[i + 1][1], t, noise, caption_dropout=0.0)
+                    losses.append(None)             # placeholder: the read-back below must still see step i's loss
+                    torch.cuda.current_stream().synchronize()
+                    losses[-1] = loss.item()
+                else:
+                    losses.append(loss.item())
+        results.append(losses)
+    l0, l1 = results
+    assert len(l0) == len(l1) == 6
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 2e-3 * abs(a), (l0, l1)
+    assert len({round(x, 4) for x in l0}) > 3       # the steps really differ
