@@ -93,3 +93,16 @@ def test_attn_bwd_tail_plan_covers_every_pair_once_and_balances():
         if (P, nq, C) == (42, 129, 74):                   # the debug-8k self-attention tail: uniform 3-way split = 2 x (43 + 10)
             assert makespan <= 95.0
     assert L.vds_attn_bwd_tail_plan(42, 129, 74, buf, 4) == 0      # too small a table: unsplit
+
+
+def test_wgrad_split_model_reproduces_the_measured_optima():
+    """engine.wgrad_splits: host-side cost model of the split-K factor of the wgrad GEMMs; the factors below are the
+    measured optima of scripts/wgrad_splits_bench.py on a B200 (debug-8k, DiT-B and DiT-XL token counts)."""
+    import vds_b200  # noqa: F401
+    from vds_b200.engine import wgrad_splits as w
+    assert [w(1536, 512, 16416), w(2048, 512, 16416), w(512, 2048, 16416), w(512, 512, 16416)] == [12, 9, 9, 9]
+    assert [w(1536, 512, 2176), w(2048, 512, 2176), w(512, 2048, 2176), w(512, 512, 2176)] == [3, 2, 2, 9]
+    assert [w(1536, 512, 4128), w(2048, 512, 4128), w(512, 512, 4128)] == [3, 2, 9]
+    assert w(24576, 4096, 1024) == 1                  # the grouped context_kv wgrad: hundreds of tiles, nothing to split
+    for args in [(128, 128, 64), (512, 512, 100), (3456, 1152, 4128)]:
+        assert 1 <= w(*args) <= max(1, (args[2] + 63) // 64)

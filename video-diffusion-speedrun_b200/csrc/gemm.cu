@@ -35,7 +35,8 @@ struct GemmCfg {
 
 template <int BN, bool A_MN, bool B_MN, int EPI, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const GemmDev p, int tma_c) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -43,14 +44,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t smem_base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - raw_addr);
 
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES;   // behind the staging tiles (those are 1024-byte aligned: TMA swizzle atom)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STG_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -192,18 +193,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t t_base = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
       constexpr bool kF32 = (EPI == VDS_EPI_ACCUM_F32 || EPI == VDS_EPI_STORE_F32);
       if constexpr (kF32) {
+        uint8_t* stg = smem_gen + STAGES * Cfg::STAGE_BYTES + (warp - 2) * 4096;
 #pragma unroll 1
         for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
           uint32_t v[32];
           tmem_ld32(t_base + c * 32, v);
           tmem_ld_wait();
-          epilogue_row<EPI>(p, row, nt * BN + c * 32, v);
+          if (EPI == VDS_EPI_ACCUM_F32 && tma_c) accum_f32_tma(&tmC, stg, mt * BM + q * 32, nt * BN + c * 32, v, lane);
+          else epilogue_row<EPI>(p, row, nt * BN + c * 32, v);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
       } else {
-        uint8_t* stg = smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + (warp - 2) * 4096;
+        uint8_t* stg = smem_gen + STAGES * Cfg::STAGE_BYTES + (warp - 2) * 4096;
         constexpr int GROUPS = BN / 128;   // 64-column groups per warp (its half of the tile)
 #pragma unroll 1
         for (int gi = 0; gi < GROUPS; ++gi) {
@@ -223,6 +226,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
 
+  if (warp >= 2 && lane == 0) bulk_wait_group0();   // TMA reductions of the fp32 epilogue complete before the CTA exits
   tc_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();   // nobody exits while the peer may still multicast / arrive here
@@ -245,6 +249,12 @@ static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
     else       { dims[0] = a.N; dims[1] = a.K; box[0] = 64; box[1] = BK; }
     strides[0] = (uint64_t)a.ldb * 2;
     r = encode_tmap_bf16(&tmB, a.B, 2, dims, strides, box);
+    if (r) return r;
+  }
+  CUtensorMap tmC = tmA;
+  int tma_c = 0;
+  if (EPI == VDS_EPI_ACCUM_F32) {
+    int r = make_tmap_accum_f32(&tmC, a.C, a.ldc, a.M, a.N, &tma_c);
     if (r) return r;
   }
   GemmDev p;
@@ -278,7 +288,7 @@ static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
   const int max_clusters = num_sms() / CL;
   const int grid = (int)(total < max_clusters ? total : max_clusters) * CL;
   if constexpr (CL == 1) {
-    launch_k(kern, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, p);
+    launch_k(kern, grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, p, tma_c);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -294,7 +304,7 @@ static int launch_gemm(const vds_gemm_args& a, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p, tma_c);
     if (e != cudaSuccess) {
       set_error("gemm: cluster launch failed: %s", cudaGetErrorString(e));
       return VDS_ERR_CUDA;

@@ -616,7 +616,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           uint32_t v[32];
           tmem_ld32(t_base + c * 32, v);
           tmem_ld_wait();
-          epilogue_row<EPI>(p, row, nt * G2_BN + c * 32, v);
+          if (EPI == VDS_EPI_ACCUM_F32 && tma_c)
+            accum_f32_tma(&tmC, smem_gen + G2_STAGES * G2_STAGE + (warp - 2) * 4096, mt * BM + q * 32, nt * G2_BN + c * 32, v, lane);
+          else
+            epilogue_row<EPI>(p, row, nt * G2_BN + c * 32, v);
         }
         tc_fence_before();
         __syncwarp();
@@ -691,6 +694,10 @@ static int launch_gemm2(const vds_gemm_args& a, cudaStream_t stream) {
       if (r) return r;
       tma_c2 = 1;
     }
+  }
+  if (EPI == VDS_EPI_ACCUM_F32) {   // split-K wgrad: fp32 tiles added into C by the TMA unit
+    int r = make_tmap_accum_f32(&tmC, a.C, a.ldc, a.M, a.N, &tma_c);
+    if (r) return r;
   }
   // fused fast path: every bf16 operand / output of the epilogue reachable by TMA (no row remap, 16-byte aligned)
   CUtensorMap tmAux = tmA;

@@ -1,6 +1,8 @@
 // Shared by gemm.cu (1-CTA tiles) and gemm2.cu (2-CTA cta_group::2 tiles): device-side argument block and the
 // fused epilogues (thread == accumulator row, coalesced through a per-warp swizzled smem transpose).
 #pragma once
+#include <stdlib.h>
+#include <string.h>
 #include "common.h"
 #include "ptx.cuh"
 
@@ -325,6 +327,39 @@ __device__ __forceinline__ void epilogue_group64(const GemmDev& p, uint8_t* stg,
     atomicAdd((unsigned long long*)p.dbg + 10, (unsigned long long)(tq3 - tq2));
     atomicAdd((unsigned long long*)p.dbg + 11, (unsigned long long)(clock64() - tq3));
   }
+}
+
+// fp32 accumulate (VDS_EPI_ACCUM_F32: wgrad split-K) of one warp's 32 rows x 32 columns: transposed through the warp's
+// 4 KiB staging tile (thread = row -> 128-byte rows, XOR swizzle == TMA 128-byte swizzle) and added into C by the TMA unit
+// (cp.reduce.async.bulk.tensor .add.f32).  Per-thread red.global.add.v4 of row-major data touches 32 lines per warp
+// instruction: 64 of them per thread made the epilogue of one 256 x 256 split ~9 us (scripts/wgrad_splits_bench.py).
+// Rows / columns past the matrix are clipped by the tensor map.
+__device__ __forceinline__ void accum_f32_tma(const CUtensorMap* tmC, uint8_t* stg, int row0, int col0,
+                                              const uint32_t (&v)[32], int lane) {
+  if (lane == 0) bulk_wait_group_read0();      // the previous reduction has finished reading the tile
+  __syncwarp();
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<uint4*>(stg + stg_off(lane, g)) = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_reduce_add_2d(tmC, smem_u32(stg), col0, row0);
+    bulk_commit_group();
+  }
+}
+// tensor map of an fp32 accumulation target C[M, ldc] for accum_f32_tma (box 32 x 32, 128-byte swizzle); *ok = 0 when C
+// does not qualify (alignment): the kernels then fall back to per-thread red.global.add
+static inline int make_tmap_accum_f32(CUtensorMap* tm, const void* C, long long ldc, int M, int N, int* ok) {
+  *ok = 0;
+  static const bool env_on = getenv("VDS_GEMM_TMA_RED") == nullptr || strcmp(getenv("VDS_GEMM_TMA_RED"), "0") != 0;   // tuning switch
+  if (!env_on || C == nullptr || ldc % 4 != 0 || ((uintptr_t)C & 15) != 0) return VDS_OK;
+  uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, strides[1] = {(uint64_t)ldc * 4};
+  uint32_t box[2] = {32, 32};
+  int r = encode_tmap(tm, C, 1, 2, dims, strides, box, 1);
+  if (r) return r;
+  *ok = 1;
+  return VDS_OK;
 }
 
 // One thread handles 32 consecutive columns [col0, col0+32) of output row `row`.

@@ -222,6 +222,30 @@ def _forward(model, P, x, context, timesteps, save=True, rope_starts=None, noise
     return out, c
 
 
+def wgrad_splits(n_out, n_in, rows, sms=148):
+    """Split-K factor of a wgrad GEMM dW[n_out, n_in] += dy[rows, n_out]^T x[rows, n_in] (contraction over the tokens).
+
+    Host-side cost model of the two tile paths of vds_gemm, fitted to scripts/wgrad_splits_bench.py on a B200: a work item
+    (one output tile x one k-range) costs 0.25 us per 64-row k-block — a 128 x 128 tile on one SM and a 256 x 256 tile on
+    an SM pair take the same time per k-block — plus a fixed 5.3 us (1-CTA) / 6.3 us (2-CTA: fp32 reduction of a 4 x larger
+    tile); the 2-CTA path is taken when tiles x splits fill half the SM pairs (gemm.cu: vds_gemm).  Best is usually the
+    factor that makes ~148 items: one round of 1-CTA tiles or two rounds of pair tiles."""
+    kb = max(1, (rows + 63) // 64)
+    t128 = ((n_out + 127) // 128) * ((n_in + 127) // 128)
+    pt = ((n_out + 255) // 256) * ((n_in + 255) // 256)
+    two_cta_ok = n_in % 64 == 0 and n_in >= 256
+    best, best_cost = 1, None
+    for s in range(1, min(24, kb) + 1):
+        per = -(-kb // s)
+        if two_cta_ok and pt * s >= sms // 2:
+            cost = -(-pt * s // (sms // 2)) * (per * 0.25 + 6.3)
+        else:
+            cost = -(-t128 * s // sms) * (per * 0.25 + 5.3)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = s, cost
+    return best
+
+
 class GradSink:
     """Where parameter gradients go: name -> fp32 tensor of the parameter's shape (accumulated into)."""
 
@@ -245,7 +269,7 @@ class GradSink:
         w = self.buf(name)
         w2 = w.view(w.shape[0], -1)
         K = dy.shape[0] if rows is None else rows
-        splits = max(1, min(16, K // 2048))
+        splits = wgrad_splits(w2.shape[0], w2.shape[1], K)
         ops.gemm(dy, x, a_mn=True, b_mn=True, epilogue=L.EPI_ACCUM_F32, out=w2, splits=splits, K=K)
 
     def bgrad(self, name, dy):
