@@ -44,7 +44,8 @@ constexpr int FWD_SMEM = 6 * TILE_BYTES + 256 + 1024;
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttnFwdParams p,
+                int tma_o) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -278,22 +279,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after();
     const int row = q0 + t * 128 + r;
     const float inv_l = 1.0f / l_run;
+    // O leaves through this tile's Q operand tile (every MMA that read it is complete: o_done) in the same two-halves
+    // SW128 image and one TMA store per half; per-thread row stores are 32 partial-sector transactions per warp
+    // instruction (the whole epilogue of a short cross-attention CTA).  Rows past Lq are clipped by the tensor map.
+    uint8_t* otile = gen + t * TILE_BYTES;
 #pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
       tmem_ld32(tO + c * 32, v);
       tmem_ld_wait();
-      if (row < p.Lq) {
-        bf16* dst = p.out + ((long long)b * p.Lq + row) * p.ldo + head * HD + c * 32;
+      bf16* dst = p.out + ((long long)b * p.Lq + min(row, p.Lq - 1)) * p.ldo + head * HD + c * 32;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
-          u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
-          u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
-          u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(dst + g * 8) = u;
-        }
+      for (int g = 0; g < 4; ++g) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv_l, __uint_as_float(v[g * 8 + 1]) * inv_l);
+        u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv_l, __uint_as_float(v[g * 8 + 3]) * inv_l);
+        u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv_l, __uint_as_float(v[g * 8 + 5]) * inv_l);
+        u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv_l, __uint_as_float(v[g * 8 + 7]) * inv_l);
+        if (tma_o) st_tile8(otile, r, c * 32 + g * 8, u);
+        else if (row < p.Lq) *reinterpret_cast<uint4*>(dst + g * 8) = u;
+      }
+    }
+    if (tma_o) {
+      fence_proxy_async_smem();
+      named_bar_sync(1 + t, 128);
+      if (r == 0 && q0 + t * 128 < p.Lq) {
+        tma_store_4d(&tmO, sQ + t * TILE_BYTES, 0, q0 + t * 128, head, b);
+        tma_store_4d(&tmO, sQ + t * TILE_BYTES + HALF_BYTES, 64, q0 + t * 128, head, b);
+        bulk_commit_group();
+        bulk_wait_group0();
       }
     }
     if (row < p.Lq && p.lse != nullptr) p.lse[((long long)b * p.nh + head) * p.Lq + row] = m_run + log2f(l_run);
@@ -842,7 +856,13 @@ int vds_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   p.out = (bf16*)out; p.ldo = ldo; p.lse = lse; p.Lq = Lq; p.Lk = Lk; p.nh = nh;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((Lq + 255) / 256, nh, B);
-  launch_k(attn_fwd_kernel, grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream, tq, tk, tv, p);
+  CUtensorMap to = tq;
+  int tma_o = 0;
+  if (((uintptr_t)out & 15) == 0 && ldo % 8 == 0) {   // else: per-thread row stores
+    if ((r = make_tmap_tokens(&to, out, ldo, Lq, nh, B))) return r;
+    tma_o = 1;
+  }
+  launch_k(attn_fwd_kernel, grid, FWD_THREADS, FWD_SMEM, (cudaStream_t)stream, tq, tk, tv, to, p, tma_o);
   VDS_CHECK_LAUNCH("attn_fwd");
   return VDS_OK;
 }
