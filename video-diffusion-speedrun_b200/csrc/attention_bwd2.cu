@@ -624,7 +624,18 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint32_t v[32];
       tmem_ld32(t + c * 32, v);
       tmem_ld_wait();
-      if (split_mode) {   // partial sums over this cluster's query range: fp32 red into the compact workspace (fixed up to bf16 later)
+      if (split_mode && pp.tma_dkdv) {
+        // partial sums over this piece's query range, added into the compact fp32 workspace by the TMA unit (fixed up to
+        // bf16 later): the 128 x 128 fp32 tile is staged as four [128 rows x 32 floats] SW128 boxes — dK over the K / V operand
+        // tiles, dV over the Q / dO stages, all free once mma_done has fired (K^T and the dS^T sets are still read by the last
+        // dQ^T).  Rows of kv positions past Lk are exact zeros (P^T and dS^T are masked), so the whole tile may be added.
+        uint8_t* box = gen + (which == 0 ? B2_OFF_K : B2_OFF_ROWS) + c * 16384;
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(box + sw128_offset(r, g)) =
+              make_float4(__uint_as_float(v[g * 4]) * osc, __uint_as_float(v[g * 4 + 1]) * osc,
+                          __uint_as_float(v[g * 4 + 2]) * osc, __uint_as_float(v[g * 4 + 3]) * osc);
+      } else if (split_mode) {   // (workspace not TMA-able) per-thread fp32 red
         if (krow < p.Lk) {
           float* dst = pp.compact + (((long long)pair_local * 2 + crank) * 2 + which) * (128 * HD) + r * HD + c * 32;
 #pragma unroll
@@ -660,6 +671,18 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * osc, __uint_as_float(v[g * 8 + 7]) * osc);
           *reinterpret_cast<uint4*>(dst + g * 8) = u;
         }
+      }
+    }
+    if (split_mode && pp.tma_dkdv) {
+      fence_proxy_async_smem();
+      named_bar_sync(3 + which, 128);
+      if (quad == 0 && lane == 0 && kv0 < p.Lk) {   // a phantom tile adds nothing
+        const uint32_t tile = which == 0 ? sK : sROWS;
+        const int row0 = ((pair_local * 2 + (int)crank) * 2 + which) * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_reduce_add_2d(&tmDK, tile + c * 16384, c * 32, row0);
+        bulk_commit_group();
+        bulk_wait_group0();
       }
     }
     if (!split_mode && pp.tma_dkdv) {
@@ -706,6 +729,14 @@ int launch_attn_bwd_pairs(const void* q, int64_t ldq, const void* k, int64_t ldk
   const bool tma_out = tma_env && n_pieces == 0 && p0.dk != nullptr && p0.dv != nullptr && ((uintptr_t)p0.dk & 15) == 0 &&
                        ((uintptr_t)p0.dv & 15) == 0 && p0.lddk % 8 == 0 && p0.lddv % 8 == 0;
   tdk = tk; tdv = tv;
+  bool tma_compact = false;
+  if (tma_env && n_pieces > 0 && compact != nullptr && ((uintptr_t)compact & 15) == 0) {
+    // compact workspace [n_pairs * 2 tiles][dk | dv][128][128] fp32 as one 2-D matrix of 128 columns: box = 128 rows x 32 floats
+    uint64_t cdims[2] = {(uint64_t)HD, (uint64_t)n_pairs * 2 * 2 * 128}, cstr[1] = {(uint64_t)HD * 4};
+    uint32_t cbox[2] = {32, 128};
+    if ((r = encode_tmap(&tdk, compact, 1, 2, cdims, cstr, cbox, 1))) return r;
+    tma_compact = true;
+  }
   if (tma_out) {
     if ((r = make_tmap_tokens(&tdk, p0.dk, p0.lddk, Lk, nh, B))) return r;
     if ((r = make_tmap_tokens(&tdv, p0.dv, p0.lddv, Lk, nh, B))) return r;
@@ -722,7 +753,7 @@ int launch_attn_bwd_pairs(const void* q, int64_t ldq, const void* k, int64_t ldk
   pp.pair_base = pair_base;
   pp.pairs_per_bh = pairs_per_bh;
   pp.n_pieces = n_pieces;
-  pp.tma_dkdv = tma_out ? 1 : 0;
+  pp.tma_dkdv = (tma_out || tma_compact) ? 1 : 0;
   pp.compact = compact;
   for (int i = 0; i < n_pieces; ++i) pp.pieces[i] = pieces[i];
   for (int i = n_pieces; i < VDS_BWD2_MAX_PIECES; ++i) pp.pieces[i] = 0u;
