@@ -368,7 +368,10 @@ constexpr int BWD_SMEM = BWD_OFF_BAR + 256 + 1024;
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                const __grid_constant__ CUtensorMap tmDQ, const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmKo,
+                const __grid_constant__ CUtensorMap tmVo, const AttnBwdParams p, int out_mode) {
+  // out_mode: how dK / dV leave — 0 per-thread stores / red.global; 1 bf16 TMA store (tmKo / tmVo over dk / dv);
+  // 2 fp32 TMA reduce-add into dk_acc / dv_acc (tmKo / tmVo); 3 fp32 TMA reduce-add into the compact workspace (tmKo)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -677,12 +680,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       const int krow = kv0 + r;
       const uint32_t t = (which == 0 ? tDK : tDV) + lane_off;
+      // Every MMA of this CTA is complete (mma_done of the last sub-tile), so the operand tiles are free: with out_mode != 0
+      // the tile is staged there (dK over K | V, dV over the Q / dO ring) in TMA box images and leaves by one bulk tensor
+      // store / reduce-add per box — row-per-thread global accesses cost 32 line look-ups per warp instruction.
+      uint8_t* stage = gen + (which == 0 ? 0 : BWD_OFF_Q);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld32(t + c * 32, v);
         tmem_ld_wait();
-        if (krow < p.Lk) {
+        if (out_mode == 1) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+            u.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+            u.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+            u.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+            st_tile8(stage, r, c * 32 + g * 8, u);
+          }
+        } else if (out_mode >= 2) {   // fp32: four [128 rows x 32 floats] SW128 boxes; rows past Lk hold exact zeros
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(stage + c * 16384 + sw128_offset(r, g)) =
+                make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                            __uint_as_float(v[g * 4 + 3]));
+        } else if (krow < p.Lk) {
           if (p.q_splits == 1) {
             bf16* dst = (which == 0 ? p.dk + ((long long)b * p.Lk + krow) * p.lddk
                                     : p.dv + ((long long)b * p.Lk + krow) * p.lddv) + head * HD + c * 32;
@@ -707,6 +730,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                            "f"(__uint_as_float(v[g * 4 + 2])), "f"(__uint_as_float(v[g * 4 + 3]))
                            : "memory");
           }
+        }
+      }
+      if (out_mode != 0) {
+        fence_proxy_async_smem();
+        named_bar_sync(3 + which, 128);
+        if (quad == 0 && lane == 0 && kv0 < p.Lk) {
+          const uint32_t st = base + (which == 0 ? 0 : BWD_OFF_Q);
+          const CUtensorMap* tm = (which == 0 || out_mode == 3) ? &tmKo : &tmVo;
+          if (out_mode == 1) {
+            tma_store_4d(tm, st, 0, kv0, head, b);
+            tma_store_4d(tm, st + HALF_BYTES, 64, kv0, head, b);
+          } else if (out_mode == 2) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_reduce_add_4d(tm, st + c * 16384, c * 32, kv0, head, b);
+          } else {
+            const int row0 = (item_local * 2 + which) * 128;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_reduce_add_2d(tm, st + c * 16384, c * 32, row0);
+          }
+          bulk_commit_group();
+          bulk_wait_group0();
         }
       }
     }
@@ -934,6 +978,39 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
   // `rem` items (local indices 0..rem-1 under the indexing already set in p) on the 1-CTA kernel.  With a workspace and
   // a long query range they are split `s` ways along the query range (fp32 red into a compact workspace + a bf16
   // fix-up), so a partly filled last wave costs ceil(rem*s/SMs)/s waves instead of 1.
+  // one launch of the 1-CTA kernel; picks how dK / dV leave (see attn_bwd_kernel: out_mode)
+  static const bool tma_env = getenv("VDS_BWD_TMA_OUT") == nullptr || strcmp(getenv("VDS_BWD_TMA_OUT"), "0") != 0;   // tuning switch
+  auto launch_1cta = [&](const AttnBwdParams& pk, int items) -> int {
+    CUtensorMap tko = tk, tvo = tv;
+    int out_mode = 0, rr;
+    auto al16 = [](const void* ptr) { return ptr != nullptr && ((uintptr_t)ptr & 15) == 0; };
+    if (tma_env && pk.q_splits == 1) {
+      if (al16(pk.dk) && al16(pk.dv) && pk.lddk % 8 == 0 && pk.lddv % 8 == 0) {
+        if ((rr = make_tmap_tokens(&tko, pk.dk, pk.lddk, Lk, nh, B))) return rr;
+        if ((rr = make_tmap_tokens(&tvo, pk.dv, pk.lddv, Lk, nh, B))) return rr;
+        out_mode = 1;
+      }
+    } else if (tma_env && pk.compact_acc != nullptr) {
+      if (al16(pk.compact_acc)) {
+        uint64_t cdims[2] = {(uint64_t)HD, (uint64_t)items * 2 * 128}, cstr[1] = {(uint64_t)HD * 4};
+        uint32_t cbox[2] = {32, 128};
+        if ((rr = encode_tmap(&tko, pk.compact_acc, 1, 2, cdims, cstr, cbox, 1))) return rr;
+        out_mode = 3;
+      }
+    } else if (tma_env) {
+      if (al16(pk.dk_acc) && al16(pk.dv_acc) && pk.ldkv_acc % 4 == 0) {
+        uint64_t dims[4] = {(uint64_t)HD, (uint64_t)Lk, (uint64_t)nh, (uint64_t)B};
+        uint64_t strides[3] = {(uint64_t)pk.ldkv_acc * 4, (uint64_t)HD * 4, (uint64_t)Lk * (uint64_t)pk.ldkv_acc * 4};
+        uint32_t box[4] = {32, 128, 1, 1};
+        if ((rr = encode_tmap(&tko, pk.dk_acc, 1, 4, dims, strides, box, 1))) return rr;
+        if ((rr = encode_tmap(&tvo, pk.dv_acc, 1, 4, dims, strides, box, 1))) return rr;
+        out_mode = 2;
+      }
+    }
+    launch_k(attn_bwd_kernel, items * pk.q_splits, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, tdq, tko, tvo, pk, out_mode);
+    VDS_CHECK_LAUNCH("attn_bwd");
+    return VDS_OK;
+  };
   auto launch_items = [&](int rem, bool allow_split) -> int {
     int tail_s = 0;
     if (allow_split && tail_ws != nullptr && rem > 0 && rem % sms != 0 && n_qsub >= 32 &&
@@ -946,15 +1023,12 @@ int vds_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const v
     }
     if (tail_s == 0) {
       if (p.rem_pair_base >= 0) p.dbg = nullptr;
-      launch_k(attn_bwd_kernel, rem * p.q_splits, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, tdq, p);
-      VDS_CHECK_LAUNCH("attn_bwd");
-      return VDS_OK;
+      return launch_1cta(p, rem);
     }
     AttnBwdParams ps = p;
     ps.q_splits = tail_s; ps.compact_acc = (float*)tail_ws;
     if (p.rem_pair_base >= 0) ps.dbg = nullptr;   // the trace buffer belongs to the pair kernel of this call
-    launch_k(attn_bwd_kernel, rem * tail_s, BWD_THREADS, BWD_SMEM, st, tq, tk, tv, tdo, tdq, ps);
-    VDS_CHECK_LAUNCH("attn_bwd");
+    { const int rl = launch_1cta(ps, rem); if (rl) return rl; }
     launch_k(attn_bwd_tail_fixup_kernel, rem * FIXUP_SPLIT, 256, 0, st, (float*)tail_ws, (bf16*)dk, lddk, (bf16*)dv, lddv, ps, Lk);
     VDS_CHECK_LAUNCH("attn_bwd_tail_fixup");
     return VDS_OK;
