@@ -432,9 +432,9 @@ def run_ours(args):
     def e2e_step_pipelined(i):
         # software pipeline of a training loop on a captured step: launch step i (staged one iteration ago), prepare
         # step i+1 on the host while the GPU computes (its copies queue behind the replay), then read step i's loss
-        loss = run.stepper.replay()
+        run.stepper.replay()                     # two graph launches: forward + loss | backward + optimizer
         stage_next(i + 1)
-        last["loss"] = loss.item()               # D2H read of THIS step's result inside the timed region
+        last["loss"] = run.stepper.loss_value()  # D2H read of THIS step's loss (final once the forward graph is done)
 
     if pipelined:
         stage_next(0)
@@ -534,8 +534,10 @@ def run_ours(args):
                          "kernel_share_of_step": kern_ms * depth / step_ms},
             "e2e": {"value": world * B * N / (e2e_ms * 1e-3), "unit": "latent tokens/s", "ms_per_step": e2e_ms,
                     "pipeline": ("step i+1 staged on the host (H2D copy waited for, inputs / RoPE offsets / optimizer scalars "
-                                 "copied into the graph's buffers) behind the replay of step i; loss of step i read back "
-                                 "before step i+1 is launched") if pipelined else "stage, launch, read back, in sequence",
+                                 "copied into the graph's buffers) behind the replay of step i; the step is two graphs "
+                                 "(forward + loss | backward + optimizer) and the loss of step i is read back over a side "
+                                 "stream as soon as the first has run, before step i+1 is launched behind the second"
+                                 ) if pipelined else "stage, launch, read back, in sequence",
                     "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": 4, "last_loss": last.get("loss")},
             "gpu_launches": int(round(launches_per_step * args.steps)),
             "cuda_graph": used_graph, "graph_error": graph_error, "issue_mode_probe": pick, "clocks": sampler.summary(),

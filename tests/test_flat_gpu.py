@@ -152,11 +152,12 @@ def test_graphed_step_stage_replay_pipeline(cuda_dev):
                 if i + 1 < 6:                       # host side of the next step, queued behind the running replay
                     torch.manual_seed(200 + i + 1)
                     stepper.stage(batches[i + 1][0], batches[i + 1][1], t, noise, caption_dropout=0.0)
-                    losses.append(None)             # placeholder: the read-back below must still see step i's loss
-                    torch.cuda.current_stream().synchronize()
-                    losses[-1] = loss.item()
+                    # early read-back over the side stream (the backward graph of step i may still be running): it must
+                    # see step i's loss although step i+1's inputs are already queued
+                    losses.append(stepper.loss_value())
+                    assert abs(losses[-1] - loss.item()) == 0.0
                 else:
-                    losses.append(loss.item())
+                    losses.append(stepper.loss_value())
         results.append(losses)
     l0, l1 = results
     assert len(l0) == len(l1) == 6

@@ -111,17 +111,24 @@ class GraphedTrainStep:
         self.hyper_dev = torch.zeros(34, device=dev, dtype=torch.float32)
         B, C, T, H, W = latent_shape
         self.thw = (T // model.time_patch_size, H // model.patch_size, W // model.patch_size)
-        self.graph = None
+        self.graph = None        # forward + loss
+        self.graph_b = None      # backward + optimizer (same memory pool)
+        self._carry = None       # tensors that live across the two graphs (d_out, saved activations, parameter views)
         self.loss = None
         self.warmup = warmup
         self.calls = 0
         self.launches_per_step = 0
         self._side = None
+        self._loss_ready = None  # recorded between the two graph launches: the loss is final once the first graph is done
+        self._rd_stream = None
+        self._loss_host = None
 
     def close(self):
         """Drops the captured graph (and its private memory pool).  Required before ``dist.destroy_process_group()``
         at world size > 1: a live graph that contains NCCL kernels keeps the communicator busy and the destroy hangs."""
         self.graph = None
+        self.graph_b = None
+        self._carry = None
         self.loss = None
         import gc
         gc.collect()
@@ -136,9 +143,9 @@ class GraphedTrainStep:
         hyper = torch.tensor(self.opt.hyper_values(self.opt._step + 1), dtype=torch.float32).pin_memory()
         self.hyper_dev.copy_(hyper, non_blocking=True)
 
-    def _step_body(self):
-        """The step without torch.autograd in the loop (the engine's forward / backward are called directly), so the
-        capture contains only our kernels + memsets and no autograd-engine stream bookkeeping."""
+    def _fwd_body(self):
+        """Forward + loss, without torch.autograd in the loop (the engine is called directly), so the capture contains only
+        our kernels + memsets and no autograd-engine stream bookkeeping."""
         model, eng = self.model, self._engine
         sharded = model._flat.world > 1
         with torch.no_grad():
@@ -150,9 +157,19 @@ class GraphedTrainStep:
                                  rope_starts_dev=self.starts_dev)
             loss, d_out, lb = ops.loss_fwd_bwd(self.latent, self.noise, out, want_grad=True, want_batch=True)
             model.last_loss_batchwise = lb
+        return loss.view(()), (P, c, d_out)
+
+    def _bwd_body(self, carry):
+        model, eng = self.model, self._engine
+        P, c, d_out = carry
+        with torch.no_grad():
             eng.run_backward(model, P, c, d_out, None)
-            self.opt.step(gather=not sharded)    # sharded: the next step's graph gathers at its top
-        return loss.view(())
+            self.opt.step(gather=model._flat.world == 1)    # sharded: the next step's graph gathers at its top
+
+    def _step_body(self):
+        loss, carry = self._fwd_body()
+        self._bwd_body(carry)
+        return loss
 
     def stage(self, latent, context, t, noise, caption_dropout=CAPTION_DROPOUT):
         """Host side of one step: the inputs and the per-step scalars go into the graph's static buffers (stream-ordered
@@ -175,6 +192,20 @@ class GraphedTrainStep:
         finally:
             self.opt.hyper_dev = None
 
+    def loss_value(self):
+        """Host value of the last step's loss as soon as its forward graph has finished (the backward may still be
+        running): the D2H read goes over a side stream that waits only for the event between the two graph launches."""
+        if self.graph is None or self._loss_ready is None:
+            return float(self.loss.item())          # warm-up steps (not captured yet)
+        if self._rd_stream is None:
+            self._rd_stream = torch.cuda.Stream()
+            self._loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        self._rd_stream.wait_event(self._loss_ready)
+        with torch.cuda.stream(self._rd_stream):
+            self._loss_host.copy_(self.loss, non_blocking=True)
+        self._rd_stream.synchronize()
+        return float(self._loss_host)
+
     def __call__(self, latent, context, t, noise, caption_dropout=CAPTION_DROPOUT):
         self.stage(latent, context, t, noise, caption_dropout)
         return self.replay()
@@ -194,15 +225,24 @@ class GraphedTrainStep:
                 cur.wait_stream(self._side)
                 return loss
             from . import lib as _lib
-            self.graph = torch.cuda.CUDAGraph()
+            # Two graphs over one memory pool: forward + loss | backward + optimizer.  The loss is final when the first
+            # one has run, so a loop can read it back (loss_value) while the backward is still executing and launch the
+            # next step behind it — the GPU never waits for the host's per-step read-back.
+            self.graph, self.graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             step_before = self.opt._step
             n0 = _lib.launch_count()
             # thread_local: NCCL's watchdog thread may touch the CUDA runtime while this thread captures
             with torch.cuda.graph(self.graph, stream=self._side, capture_error_mode="thread_local"):
-                self.loss = self._step_body().detach()
-            self.launches_per_step = _lib.launch_count() - n0   # kernels of ours inside one replay
+                loss, self._carry = self._fwd_body()
+                self.loss = loss.detach()
+            with torch.cuda.graph(self.graph_b, pool=self.graph.pool(), stream=self._side, capture_error_mode="thread_local"):
+                self._bwd_body(self._carry)
+            self.launches_per_step = _lib.launch_count() - n0   # kernels of ours inside one replay of both
             self.opt._step = step_before              # capture does not execute; the replay below is the real step
+            self._loss_ready = torch.cuda.Event()
         self.graph.replay()
+        self._loss_ready.record()
+        self.graph_b.replay()
         self.opt._step += 1
         flat = self.model._flat
         flat._gather_pending = flat.world > 1    # the replayed step ended with an un-gathered optimizer update
