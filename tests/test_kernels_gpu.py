@@ -437,3 +437,17 @@ def test_gemm_qkv_rope_epilogue(cuda_dev, M_B_L_nh_K, use_bias, mix):
     k = rearrange(qkv0[:, h:2 * h].view(B, Lr, h), "b l (h d) -> b h l d", h=nh)
     rk = rearrange(_ref_rope(k, cos[None, None], sin[None, None]), "b h l d -> (b l) (h d)")
     _close(qkv_f[:, h:2 * h], rk, tol=1e-2)
+
+
+def test_rope_pack_layout(cuda_dev):
+    """vds_rope_pack: [L, 64] cos / sin rows -> [L + 32, 4, 32] = per 16-pair step [16 cos | 16 sin], the last 32 rows wrapping
+    around to rows 0..31 (a 32-token TMA box of the fused QKV epilogue may cross a sample boundary).  Bit-exact."""
+    from vds_b200 import ops
+    for Lr in (80, 272, 8208):
+        ang = _r((Lr, 64), cuda_dev, 50 + Lr % 7, 3.0, torch.float32)
+        cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+        tab = ops.rope_pack(cos, sin)
+        ref = torch.cat([cos.view(Lr, 4, 16), sin.view(Lr, 4, 16)], dim=2)
+        assert tab.shape == (Lr + 32, 4, 32)
+        assert torch.equal(tab[:Lr], ref)
+        assert torch.equal(tab[Lr:], ref[:32])
